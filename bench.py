@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- SpMM GFLOP/s (2*nnz*N) + HBM GB/s (% roofline) vs cuSPARSE, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload NAME] [--format csr|coo|ell] [--variant V] [--gather]
+
+A "step" is one C = A*B over the workload.  Default workload: large_25605 (25605^2, 90 % sparse,
+N = 512, CSR) -- the configuration BASELINE.json's target is quoted on; it fits one GPU.
+N > 1 (launched by torchrun, one rank per GPU): weak scaling -- every rank owns one row panel of
+25605 rows of a (N*25605) x 25605 matrix (its own seed), B is replicated, no data-path collective
+(rows of C are independent: src/spmm/csr/spmm_csr.cpp:15-27); --gather adds an NCCL all_gather of C.
+
+Timing: CUDA events on the launching stream around each step, W warm-up steps first, barrier +
+synchronize on both sides, max over ranks.  A + B + C = 630 MB > the 126 MB L2, so no flush is
+needed between steps ("inputs_larger_than_l2").  `e2e` is the same multiply through the
+host-buffer C-ABI entry point (cuspmm_spmm_csr_host: pinned host operands, H2D + kernels + D2H
+inside the timed region).  `cpu_baseline` times the reference's own spmmCSRCpu (oracle/_ref) on a
+bounded row sample on this box's host cores.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "spmm_gflops"
+UNIT = "GFLOP/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def sample_rows_for_seconds(run_rows, target_s, start_rows=16, max_rows=None):
+    """Calibrate a row-sample size so that run_rows(rows) takes about target_s seconds."""
+    rows = start_rows
+    t0 = time.perf_counter(); run_rows(rows); dt = time.perf_counter() - t0
+    est = max(rows, int(rows * target_s / max(dt, 1e-6)))
+    if max_rows:
+        est = min(est, max_rows)
+    return max(est, 1)
+
+
+def cpu_reference_csr(orc, a_host, B_host, rows):
+    """The reference's own spmmCSRCpu when oracle/_ref exists (kind 'reference', 1 thread: the
+    reference is single-threaded, src/spmm/csr/spmm_csr.cpp:15-27), else the oracle port on all
+    host threads (kind 'port')."""
+    import numpy as np
+    sub = orc.CSR(rows, a_host.K, a_host.rowPtrs[:rows + 1], a_host.colIdxs[:int(a_host.rowPtrs[rows])],
+                  a_host.vals[:int(a_host.rowPtrs[rows])])
+    if orc.ref_lib() is not None:
+        t0 = time.perf_counter(); orc.spmm_csr(sub, B_host, use_ref=True); dt = time.perf_counter() - t0
+        return dt, "reference", 1, sub.nnz
+    t0 = time.perf_counter(); orc.spmm_csr(sub, B_host, omp=True); dt = time.perf_counter() - t0
+    return dt, "port", orc.lib().oracle_num_threads(), sub.nnz
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="large_25605")
+    ap.add_argument("--format", default="csr", choices=["csr", "coo", "ell"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--gather", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cusparse", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import numpy as np
+    from oracle import oracle as orc   # CPU-baseline leg only
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, orc, np)
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    b = pkg.binding
+    import importlib
+    wl = importlib.import_module("cuspmm_b200.workloads")
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = b.lib()
+
+    M, K, density, N = wl.NAMED[args.workload]
+    rp, ci, va = wl.gen_csr_device(M, K, density, seed=618 + rank)
+    Bd = wl.gen_dense_device(K, N, seed=619)          # the same B on every rank (replicated operand)
+    nnz = int(ci.numel())
+    Cd = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    flops = 2.0 * nnz * N
+
+    fmt = args.format
+    if fmt == "csr":
+        alg_bytes = wl.csr_bytes(M, K, N, nnz)
+        step = lambda: b.spmm_csr(rp, ci, va, M, K, Bd, variant=args.variant, out=Cd)
+    elif fmt == "coo":
+        rows = torch.repeat_interleave(torch.arange(M, device="cuda", dtype=torch.int32), (rp[1:] - rp[:-1]).to(torch.int64))
+        alg_bytes = wl.coo_bytes(M, K, N, nnz)
+        step = lambda: b.spmm_coo(rows, ci, va, M, K, Bd, variant=args.variant, out=Cd)
+    else:
+        sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
+        alg_bytes = wl.sell_bytes(M, K, N, int(sc.numel()), int(sp.numel()) - 1)
+        step = lambda: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=0, out=Cd)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    if args.gather and world > 1:
+        gathered = [torch.empty_like(Cd) for _ in range(world)]
+        dist.all_gather(gathered, Cd)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    L.cuspmm_reset_launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        e0.record()
+        step()
+        if args.gather and world > 1:
+            dist.all_gather(gathered, Cd)
+        e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = int(L.cuspmm_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_ms = torch.tensor([sum(per_step)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    nnz_all = torch.tensor([nnz], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nnz_all, op=dist.ReduceOp.SUM)
+    flops_all = 2.0 * float(nnz_all.item()) * N
+    value = flops_all / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    e2e = None
+    try:
+        rp_h, ci_h, va_h = rp.cpu().pin_memory(), ci.cpu().pin_memory(), va.cpu().pin_memory()
+        B_h = Bd.cpu().pin_memory()
+        C_h = torch.empty((M, N), dtype=torch.float32).pin_memory()
+        b.spmm_csr_host(rp_h, ci_h, va_h, M, K, B_h, C_h, variant=args.variant)      # warm-up (allocations)
+        barrier()
+        t0 = time.perf_counter()
+        dev_ms = 0.0
+        for _ in range(args.e2e_steps):
+            dev_ms += b.spmm_csr_host(rp_h, ci_h, va_h, M, K, B_h, C_h, variant=args.variant)
+        barrier()
+        e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        h2d = 4 * (M + 1) + 8 * nnz + 4 * K * N
+        d2h = 4 * M * N
+        e2e = {"value": flops_all / (float(e2e_ms.item()) * 1e-3) / 1e9, "unit": UNIT,
+               "ms_per_step": float(e2e_ms.item()), "device_ms_per_step": dev_ms / args.e2e_steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "cuspmm_spmm_csr_host (pinned host CSR + B in, C out; wall clock around the call)",
+               "same_result": bool((C_h.cuda() == Cd).all().item()) if fmt == "csr" else None}
+    except Exception as ex:      # report, never hide
+        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+
+    out = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        # the bounds of SURVEY.md section 8d / BASELINE.md section 3
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        t_hbm = alg_bytes / (peak * 1e9) * 1e3
+        t_fp32 = flops / (148 * 128 * 2 * sm_clock * 1e6) * 1e3
+        t_l1 = (4.0 * nnz * N) / (148 * 128 * sm_clock * 1e6) * 1e3
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {M}x{K} A, density {density} (nnz {nnz} on rank 0), "
+                                   f"B {K}x{N}, {fmt.upper()} variant {args.variant} (0 = selector)",
+                       "format": fmt, "M_per_gpu": M, "K": K, "N": N, "nnz_per_gpu": nnz,
+                       "parallelism": f"row panels x{world}, B replicated" + (", NCCL all_gather of C" if args.gather else ", C left sharded"),
+                       "l2": "inputs_larger_than_l2 (A+B+C = %.0f MB vs 126 MB L2; no flush)" % (alg_bytes / 1e6),
+                       "seed": 618},
+            "gpu_launches": launches,
+            "wall_ms_timed_region": wall_ms,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": ms_per_step,
+                         "bounds_ms": {"hbm": t_hbm, "fp32_fma": t_fp32, "smem_operand_bw": t_l1},
+                         "binding": max((("hbm", t_hbm), ("fp32_fma", t_fp32), ("smem_operand_bw", t_l1)), key=lambda x: x[1])[0],
+                         "frac_of_binding_bound": max(t_hbm, t_fp32, t_l1) / ms_per_step,
+                         "note": "fp32 CUDA-core SpMM at this density is bound by SM-local operand bandwidth (one "
+                                 "distinct B element per FMA through shared memory), not HBM: see DESIGN.md"},
+            "e2e": e2e,
+            "clocks": clocks,
+        }
+        # ---- same-run cuSPARSE baseline
+        if not args.no_cusparse and fmt in ("csr", "coo"):
+            try:
+                tmp = torch.empty_like(Cd)
+                if fmt == "csr":
+                    avg, mn = b.cusparse_spmm(0, rp, ci, va, M, K, Bd, tmp, warmup=2, iters=5)
+                else:
+                    avg, mn = b.cusparse_spmm(1, rows, ci, va, M, K, Bd, tmp, warmup=2, iters=5)
+                out["cusparse"] = {"alg": "CSR_ALG2" if fmt == "csr" else "COO_ALG4", "ms_avg": avg, "ms_min": mn,
+                                   "gflops": flops / (avg * 1e-3) / 1e9, "speedup_vs_cusparse": avg / ms_per_step,
+                                   "max_abs_diff_vs_ours": float((tmp - Cd).abs().max().item())}
+                del tmp
+            except Exception as ex:
+                out["cusparse"] = {"error": str(ex)[:200]}
+        # ---- CPU baseline: bounded row sample of the same workload, this box's host cores
+        if world == 1:
+            try:
+                rows_cap = min(M, 4096)
+                srp, sci, sva = wl.csr_sample_to_host(rp, ci, va, 0, rows_cap)
+                a_host = orc.CSR(rows_cap, K, srp, sci, sva)
+                B_host = Bd.cpu().numpy()
+                run = lambda r: cpu_reference_csr(orc, a_host, B_host, r)
+                rows_s = sample_rows_for_seconds(run, args.cpu_seconds, 8, rows_cap)
+                dt, kind, cores, snnz = run(rows_s)
+                out["cpu_baseline"] = {"value": 2.0 * snnz * N / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                       "sample": f"rows [0,{rows_s}) of the workload ({snnz} nnz, {dt:.1f} s); "
+                                                 f"oracle/_ref = the reference's spmmCSRCpu built -O2",
+                                       "host_cpus": os.cpu_count()}
+            except Exception as ex:
+                out["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def reference_arm(args, orc, np):
+    """--impl reference: the reference's own CPU SpMM (oracle/_ref, else the oracle port) on a bounded
+    row sample of the same workload per step.  Inputs are generated with numpy (same distribution,
+    same density; no GPU is touched)."""
+    from importlib import util
+    spec = util.spec_from_file_location("wl_named", os.path.join(ROOT, "cuda-optimization-for-spmm_b200", "workloads.py"))
+    # only the NAMED table is needed; avoid importing torch.cuda
+    text = open(spec.origin).read()
+    ns = {}
+    exec(text[text.index("NAMED = {"):text.index("def gen_csr_device")], ns)
+    M, K, density, N = ns["NAMED"][args.workload]
+    rng = np.random.default_rng(618)
+    rows_cap = 256
+    lens = rng.binomial(K, density, size=rows_cap)
+    rp = np.zeros(rows_cap + 1, np.uint32); rp[1:] = np.cumsum(lens)
+    ci = np.concatenate([np.sort(rng.choice(K, size=int(n), replace=False)) for n in lens]).astype(np.uint32)
+    va = rng.uniform(-1, 1, size=int(rp[-1])).astype(np.float32)
+    B = rng.uniform(-1, 1, size=(K, N)).astype(np.float32)
+    a = orc.CSR(rows_cap, K, rp, ci, va)
+    run = lambda r: cpu_reference_csr(orc, a, B, r)
+    total_steps = max(1, args.steps + args.warmup)
+    per_step_s = max(0.5, min(5.0, 150.0 / total_steps))
+    rows_s = sample_rows_for_seconds(run, per_step_s, 4, rows_cap)
+    for _ in range(args.warmup):
+        run(rows_s)
+    t = 0.0
+    kind, cores, snnz = "port", 1, 0
+    for _ in range(args.steps):
+        dt, kind, cores, snnz = run(rows_s)
+        t += dt
+    ms = t / args.steps * 1e3
+    val = 2.0 * snnz * N / (ms * 1e-3) / 1e9
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {M}x{K} A, density {density}, B {K}x{N}, CSR; each step = rows "
+                                  f"[0,{rows_s}) ({snnz} nnz) through the reference's spmmCSRCpu"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "kind": kind, "cores": cores,
+                            "sample": f"{rows_s} rows ({snnz} nnz) per step", "host_cpus": os.cpu_count()},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

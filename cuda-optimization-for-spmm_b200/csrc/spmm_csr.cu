@@ -1,0 +1,453 @@
+// spmm_csr.cu -- CSR SpMM kernels for sm_100a.
+//
+// Replaces the reference's spmmCSRK1..K4 (src/spmm/csr/spmm_csr_k{1,2,3,4}.cu).  None of
+// those designs is kept: every kernel here accumulates in fp32 with FMA in CSR order
+// (fixed order, no atomics => bit-reproducible run to run), reads B row-major with
+// 128-bit loads and never transposes B.
+//
+//   variant 1  csr_rowsplit_vec   warp per row, lanes over columns (float4), rows dealt to
+//                                 warps in nnz-balanced contiguous ranges found by an
+//                                 in-kernel 32-ary search on rowPtrs (no preprocessing pass)
+//   variant 2  csr_subwarp_vec    "vector per row": G = 4/8/16 lanes per row for narrow N
+//   variant 3  csr_staged         row panel x K-chunks; each K-chunk of B is staged in shared
+//                                 memory by TMA bulk copies (cp.async.bulk + mbarrier ring,
+//                                 one producer warp) and re-used by all rows of the panel
+//   variant 4  csr_rowsplit_scalar any N / ldb / alignment (N = 21 in data/small_210)
+#include "common.cuh"
+
+namespace cuspmm_b200 {
+
+// =============================================================== variant 1 / 4
+// items = one per row + one per non-zero; warp w owns the rows whose first item falls
+// into [w*ipw, (w+1)*ipw).  Whole rows only, so no carries between warps.
+__device__ __forceinline__ void warp_row_range(const uint32_t *__restrict__ rowPtrs, uint32_t M,
+                                               uint64_t ipw, uint32_t w, uint32_t &r0, uint32_t &r1) {
+    // rowPtrs may be a row-panel VIEW of a larger matrix (rowPtrs[0] != 0, absolute offsets
+    // into colIdxs/vals), so keys are taken relative to the panel's first entry.
+    const uint32_t first = __ldg(rowPtrs);
+    auto key = [&](uint32_t p) -> uint64_t { return (uint64_t)(__ldg(rowPtrs + p) - first) + p; };
+    r0 = warp_lower_bound(M, (uint64_t)w * ipw, key);
+    r1 = warp_lower_bound(M, (uint64_t)(w + 1) * ipw, key);
+}
+
+template <int U, int J>
+__global__ void __launch_bounds__(256)
+csr_rowsplit_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
+                        const float *__restrict__ vals, uint32_t M, uint64_t ipw,
+                        const float *__restrict__ B, uint32_t N, size_t ldb,
+                        float *__restrict__ C, size_t ldc) {
+    const uint32_t lane = lane_id();
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t col0 = blockIdx.y * (128u * U) + lane * 4u;   // first column of this lane
+    uint32_t r0, r1;
+    warp_row_range(rowPtrs, M, ipw, w, r0, r1);
+
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) valid[u] = (col0 + u * 128u) < N;
+
+    for (uint32_t r = r0; r < r1; ++r) {
+        const uint32_t start = __ldg(rowPtrs + r), end = __ldg(rowPtrs + r + 1);
+        float4 acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (uint32_t base = start; base < end; base += 32) {
+            const uint32_t idx = base + lane;
+            uint32_t mc = 0;
+            float mv = 0.f;
+            if (idx < end) { mc = ld_stream(colIdxs + idx); mv = ld_stream(vals + idx); }
+            const int cnt = min(32u, end - base);
+            int j = 0;
+            for (; j + J <= cnt; j += J) {
+                float4 b[J][U];
+                float v[J];
+#pragma unroll
+                for (int k = 0; k < J; ++k) {
+                    const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j + k);
+                    v[k] = __shfl_sync(0xFFFFFFFFu, mv, j + k);
+                    const float *brow = B + (size_t)c * ldb + col0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (valid[u]) b[k][u] = __ldg(reinterpret_cast<const float4 *>(brow + u * 128));
+                }
+#pragma unroll
+                for (int k = 0; k < J; ++k)
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (valid[u]) fma4(acc[u], v[k], b[k][u]);
+            }
+            for (; j < cnt; ++j) {
+                const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j);
+                const float v = __shfl_sync(0xFFFFFFFFu, mv, j);
+                const float *brow = B + (size_t)c * ldb + col0;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (valid[u]) fma4(acc[u], v, __ldg(reinterpret_cast<const float4 *>(brow + u * 128)));
+            }
+        }
+        float *crow = C + (size_t)r * ldc + col0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (valid[u]) __stcs(reinterpret_cast<float4 *>(crow + u * 128), acc[u]);
+    }
+}
+
+template <int U>
+__global__ void __launch_bounds__(256)
+csr_rowsplit_scalar_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
+                           const float *__restrict__ vals, uint32_t M, uint64_t ipw,
+                           const float *__restrict__ B, uint32_t N, size_t ldb,
+                           float *__restrict__ C, size_t ldc) {
+    const uint32_t lane = lane_id();
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t col0 = blockIdx.y * (32u * U) + lane;
+    uint32_t r0, r1;
+    warp_row_range(rowPtrs, M, ipw, w, r0, r1);
+    for (uint32_t r = r0; r < r1; ++r) {
+        const uint32_t start = __ldg(rowPtrs + r), end = __ldg(rowPtrs + r + 1);
+        float acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = 0.f;
+        for (uint32_t base = start; base < end; base += 32) {
+            const uint32_t idx = base + lane;
+            uint32_t mc = 0;
+            float mv = 0.f;
+            if (idx < end) { mc = ld_stream(colIdxs + idx); mv = ld_stream(vals + idx); }
+            const int cnt = min(32u, end - base);
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j);
+                const float v = __shfl_sync(0xFFFFFFFFu, mv, j);
+                const float *brow = B + (size_t)c * ldb;
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (col0 + u * 32u < N) acc[u] = fmaf(v, __ldg(brow + col0 + u * 32u), acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (col0 + u * 32u < N) C[(size_t)r * ldc + col0 + u * 32u] = acc[u];
+    }
+}
+
+// =============================================================== variant 2
+// G lanes per row (G*4 >= column tile), 32/G rows per warp; for narrow N a full warp
+// per row would leave most lanes idle.  Rows are dealt round-robin-free: row = global
+// group index (short-row regime, no balancing needed).
+template <int G>
+__global__ void __launch_bounds__(256)
+csr_subwarp_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
+                       const float *__restrict__ vals, uint32_t M,
+                       const float *__restrict__ B, uint32_t N, size_t ldb,
+                       float *__restrict__ C, size_t ldc) {
+    const uint32_t lane = lane_id();
+    const uint32_t gl = lane % G;                    // lane inside the group
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const uint32_t col = blockIdx.y * (4u * G) + gl * 4u;
+    const bool valid = col < N;
+    const uint32_t r = gid;
+    uint32_t start = 0, end = 0;
+    if (r < M) { start = __ldg(rowPtrs + r); end = __ldg(rowPtrs + r + 1); }
+    const uint32_t len = end - start;
+    const uint32_t maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t base = 0; base < maxlen; base += G) {
+        uint32_t mc = 0;
+        float mv = 0.f;
+        if (base + gl < len) { mc = ld_stream(colIdxs + start + base + gl); mv = ld_stream(vals + start + base + gl); }
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j, G);
+            const float v = __shfl_sync(0xFFFFFFFFu, mv, j, G);
+            if (valid && base + j < len)
+                fma4(acc, v, __ldg(reinterpret_cast<const float4 *>(B + (size_t)c * ldb + col)));
+        }
+    }
+    if (valid && r < M) *reinterpret_cast<float4 *>(C + (size_t)r * ldc + col) = acc;
+}
+
+// =============================================================== variant 3 (staged)
+// One CTA = NW compute warps + 1 producer warp.  The CTA owns R = NW*RW consecutive rows
+// of A and a column tile of NT columns of B/C.  K is walked in chunks of KC rows of B;
+// the producer streams chunk after chunk into a STAGES-deep shared-memory ring with TMA
+// bulk copies (cp.async.bulk.shared.global, completion on an mbarrier); each compute warp
+// consumes, for each of its RW rows, the non-zeros whose column falls inside the chunk
+// (CSR columns are sorted, so that is a contiguous run found with a per-row cursor) and
+// releases the stage.  Every B element fetched from L2 is re-used by ~R*density rows.
+// Accumulation per C element is still strictly in CSR order (chunks are visited in
+// ascending K), fp32 FMA.
+namespace staged {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();   // a lost arrive must fail loudly, not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <int NT, int NW, int RW, int KC, int STAGES>
+struct Cfg {
+    static constexpr int kNT = NT, kNW = NW, kRW = RW, kKC = KC, kStages = STAGES;
+    static constexpr int kRows = NW * RW;                     // row slots per CTA (upper bound)
+    static constexpr int kThreads = (NW + 1) * 32;            // 15 + 1 warps = 512 threads -> 128 regs/thread
+    static constexpr int kU = NT / 128;                       // float4 per lane per row
+    static constexpr size_t kStageBytes = (size_t)KC * NT * sizeof(float);
+    static constexpr size_t kSmemBytes = kStageBytes * STAGES + 2 * STAGES * sizeof(uint64_t) + 128;
+};
+
+template <class CFG>
+__global__ void __launch_bounds__(CFG::kThreads, 1)
+csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
+                  const float *__restrict__ vals, uint32_t M, uint32_t K, uint32_t rpc,
+                  const float *__restrict__ B, uint32_t N, size_t ldb,
+                  float *__restrict__ C, size_t ldc) {
+    // rpc = rows actually given to each CTA (<= kRows), chosen on the host so that the grid is a
+    // whole number of waves of the SM count
+    constexpr int NT = CFG::kNT, NW = CFG::kNW, RW = CFG::kRW, KC = CFG::kKC, STAGES = CFG::kStages;
+    constexpr int U = CFG::kU;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + CFG::kStageBytes * STAGES);
+    uint64_t *empty = full + STAGES;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t col0 = blockIdx.y * NT;                 // column tile (N % NT == 0 checked on host)
+    const uint32_t row0 = blockIdx.x * rpc;
+    const uint32_t rowEnd = min(M, row0 + rpc);
+    const uint32_t nchunks = (K + KC - 1) / KC;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ------------------------------------------------------------ producer
+        if (lane == 0) {
+            for (uint32_t ch = 0; ch < nchunks; ++ch) {
+                const uint32_t s = ch % STAGES, it = ch / STAGES;
+                if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+                const uint32_t k0 = ch * KC;
+                const uint32_t rows = min((uint32_t)KC, K - k0);
+                float *dst = tiles + (size_t)s * KC * NT;
+                mbar_expect_tx(full + s, rows * NT * (uint32_t)sizeof(float));
+                if ((size_t)NT == ldb) {       // tile rows are contiguous in B: one bulk copy
+                    bulk_g2s(dst, B + (size_t)k0 * ldb + col0, rows * NT * (uint32_t)sizeof(float), full + s);
+                } else {
+                    for (uint32_t i = 0; i < rows; ++i)
+                        bulk_g2s(dst + (size_t)i * NT, B + (size_t)(k0 + i) * ldb + col0,
+                                 NT * (uint32_t)sizeof(float), full + s);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers
+    uint32_t pos[RW], end[RW], bufbase[RW], bcol[RW];
+    float bval[RW];
+    float4 acc[RW][U];
+#pragma unroll
+    for (int i = 0; i < RW; ++i) {
+        const uint32_t r = row0 + warp * RW + i;
+        pos[i] = end[i] = 0;
+        if (r < rowEnd) { pos[i] = __ldg(rowPtrs + r); end[i] = __ldg(rowPtrs + r + 1); }
+        bufbase[i] = pos[i];
+        bcol[i] = kPad;
+        bval[i] = 0.f;
+        if (pos[i] + lane < end[i]) {
+            bcol[i] = ld_stream(colIdxs + pos[i] + lane);
+            bval[i] = ld_stream(vals + pos[i] + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[i][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    for (uint32_t ch = 0; ch < nchunks; ++ch) {
+        const uint32_t s = ch % STAGES, it = ch / STAGES;
+        const uint32_t k0 = ch * KC, k1 = k0 + KC;
+        mbar_wait(full + s, it & 1);
+        const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * KC * NT) + lane;
+#pragma unroll
+        for (int i = 0; i < RW; ++i) {
+            while (pos[i] < end[i]) {
+                uint32_t j = pos[i] - bufbase[i];
+                if (j == 32) {                       // refill the 32-entry register window
+                    bufbase[i] = pos[i];
+                    bcol[i] = kPad;
+                    bval[i] = 0.f;
+                    if (pos[i] + lane < end[i]) {
+                        bcol[i] = ld_stream(colIdxs + pos[i] + lane);
+                        bval[i] = ld_stream(vals + pos[i] + lane);
+                    }
+                    j = 0;
+                }
+                const uint32_t c = __shfl_sync(0xFFFFFFFFu, bcol[i], j);
+                if (c >= k1) break;
+                const float v = __shfl_sync(0xFFFFFFFFu, bval[i], j);
+                const float4 *brow = tile + (size_t)(c - k0) * (NT / 4);
+#pragma unroll
+                for (int u = 0; u < U; ++u) fma4(acc[i][u], v, brow[u * 32]);
+                ++pos[i];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+
+#pragma unroll
+    for (int i = 0; i < RW; ++i) {
+        const uint32_t r = row0 + warp * RW + i;
+        if (r < rowEnd) {
+            float4 *crow = reinterpret_cast<float4 *>(C + (size_t)r * ldc + col0) + lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) __stcs(crow + u * 32, acc[i][u]);
+        }
+    }
+}
+
+template <class CFG>
+int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
+           const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+    auto kern = csr_staged_kernel<CFG>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    CUSPMM_CUDA(cudaGetDevice(&dev));
+    if (!attr_done[dev & 63]) {
+        CUSPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::kSmemBytes));
+        attr_done[dev & 63] = true;
+    }
+    // whole waves: ctas = waves * SMs (per column tile), rows per CTA = ceil(M / ctas) <= kRows
+    const uint32_t sms = (uint32_t)sm_count();
+    const uint32_t minCtas = (M + CFG::kRows - 1) / CFG::kRows;
+    const uint32_t waves = (minCtas + sms - 1) / sms;
+    uint32_t ctas = waves * sms;
+    uint32_t rpc = (M + ctas - 1) / ctas;
+    if (rpc > (uint32_t)CFG::kRows) rpc = CFG::kRows;
+    if (rpc == 0) rpc = 1;
+    ctas = (M + rpc - 1) / rpc;
+    dim3 grid(ctas, N / CFG::kNT);
+    kern<<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(rowPtrs, colIdxs, vals, M, K, rpc, B, N, ldb, C, ldc);
+    CUSPMM_LAUNCH_CHECK("csr_staged_kernel");
+    return CUSPMM_OK;
+}
+
+} // namespace staged
+
+// =============================================================== host dispatch
+static bool vec_ok(const float *B, size_t ldb, const float *C, size_t ldc, uint32_t N) {
+    return (N % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
+           ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+}
+
+static uint32_t pick_warps(uint32_t M) {
+    // enough warps for ~4 resident CTAs of 8 warps on every SM, never more than one per row
+    uint64_t want = (uint64_t)sm_count() * 8 * 8;
+    return (uint32_t)(want < M ? want : (M ? M : 1));
+}
+
+int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                      uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
+                      float *C, size_t ldc, int variant, cudaStream_t st) {
+    CUSPMM_REQUIRE(variant >= 0 && variant <= CUSPMM_CSR_NUM_VARIANTS, "CSR variant %d does not exist", variant);
+    CUSPMM_REQUIRE(ldb >= N && ldc >= N, "ldb/ldc (%zu/%zu) must be >= N (%u)", ldb, ldc, N);
+    if (M == 0 || N == 0) return CUSPMM_OK;
+    CUSPMM_REQUIRE(rowPtrs && B && C && (nnz == 0 || (colIdxs && vals)), "null operand pointer");
+    const bool vok = vec_ok(B, ldb, C, ldc, N);
+
+    if (variant == 0) {   // selector: see DESIGN.md "kernel selection"
+        if (!vok) variant = 4;
+        else if (N < 128) variant = 2;
+        else {
+            const double density = (double)nnz / ((double)M * (double)K);
+            const bool staged_ok = (N % 128 == 0) && M >= 1024;
+            variant = (staged_ok && density * 64.0 >= 2.0) ? 3 : 1;
+        }
+    }
+
+    const uint32_t warps = pick_warps(M);
+    const uint64_t ipw = ((uint64_t)nnz + M + warps - 1) / warps;
+    const uint32_t blocks = (warps + 7) / 8;
+
+    switch (variant) {
+    case 1: {
+        CUSPMM_REQUIRE(vok, "variant 1 needs N %% 4 == 0 and 16-byte aligned B/C rows (N=%u ldb=%zu ldc=%zu)", N, ldb, ldc);
+        if (N > 256) {
+            dim3 grid(blocks, (N + 511) / 512);
+            csr_rowsplit_vec_kernel<4, 2><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        } else if (N > 128) {
+            dim3 grid(blocks, 1);
+            csr_rowsplit_vec_kernel<2, 4><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        } else {
+            dim3 grid(blocks, 1);
+            csr_rowsplit_vec_kernel<1, 8><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        }
+        CUSPMM_LAUNCH_CHECK("csr_rowsplit_vec_kernel");
+        return CUSPMM_OK;
+    }
+    case 2: {
+        CUSPMM_REQUIRE(vok, "variant 2 needs N %% 4 == 0 and 16-byte aligned B/C rows");
+        const uint32_t G = N <= 16 ? 4 : (N <= 32 ? 8 : 16);
+        const uint32_t rows_per_block = 256 / G;
+        dim3 grid((M + rows_per_block - 1) / rows_per_block, (N + 4 * G - 1) / (4 * G));
+        if (G == 4) csr_subwarp_vec_kernel<4><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
+        else if (G == 8) csr_subwarp_vec_kernel<8><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
+        else csr_subwarp_vec_kernel<16><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
+        CUSPMM_LAUNCH_CHECK("csr_subwarp_vec_kernel");
+        return CUSPMM_OK;
+    }
+    case 3: {
+        if (!(vok && N % 128 == 0))
+            return set_error(CUSPMM_ERR_UNSUPPORTED, "staged CSR kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
+        if (N % 512 == 0) return staged::launch<staged::Cfg<512, 15, 4, 32, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        if (N % 256 == 0) return staged::launch<staged::Cfg<256, 15, 8, 64, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        return staged::launch<staged::Cfg<128, 15, 8, 128, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    }
+    case 4: {
+        dim3 grid(blocks, (N + 127) / 128);
+        csr_rowsplit_scalar_kernel<4><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        CUSPMM_LAUNCH_CHECK("csr_rowsplit_scalar_kernel");
+        return CUSPMM_OK;
+    }
+    }
+    return set_error(CUSPMM_ERR_INVALID, "unreachable");
+}
+
+} // namespace cuspmm_b200
+
+extern "C" int cuspmm_spmm_csr(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                               uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
+                               float *C, size_t ldc, int variant, void *stream) {
+    return cuspmm_b200::spmm_csr_dispatch(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, variant,
+                                          cuspmm_b200::as_stream(stream));
+}

@@ -1,0 +1,212 @@
+/*
+ * cuspmm_b200.h -- C ABI of the B200-native SpMM engine (libcuspmm_b200.so).
+ *
+ * C = A * B, A sparse (CSR / COO / ELL / BSR), B and C dense row-major fp32.
+ * Every entry point is what the reference's host layer would bind for this path;
+ * the reference interface each one replaces is cited as file:line relative to
+ * mli43/Cuda-Optimization-for-SpMM.  Conventions:
+ *
+ *   - plain pointers and sizes only; no C++ types, no exceptions cross the ABI;
+ *   - all `*_dev` pointers are DEVICE pointers on the current device; work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ *     stream) and the call returns without synchronising unless stated;
+ *   - C is OVERWRITTEN (beta = 0); it does not have to be zeroed first;
+ *   - indices are uint32 (the reference's MT), values float (its DT);
+ *   - ldb / ldc are row strides in ELEMENTS (>= N);
+ *   - return value: 0 = CUSPMM_OK, otherwise a cuspmmStatus; the message is in
+ *     cuspmm_last_error() (thread local).  There is NO CPU fallback: without a
+ *     usable CUDA device every compute entry point fails with CUSPMM_ERR_CUDA.
+ */
+#ifndef CUSPMM_B200_H
+#define CUSPMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUSPMM_B200_VERSION 100
+
+typedef enum {
+    CUSPMM_OK = 0,
+    CUSPMM_ERR_INVALID = 1,     /* bad argument / shape / alignment */
+    CUSPMM_ERR_CUDA = 2,        /* CUDA runtime or driver error */
+    CUSPMM_ERR_UNSUPPORTED = 3, /* variant cannot run this shape (cf. spmm_csr_k4.cu:97-101) */
+    CUSPMM_ERR_WORKSPACE = 4,   /* workspace too small */
+    CUSPMM_ERR_CUSPARSE = 5     /* vendor baseline failed */
+} cuspmmStatus;
+
+/* BSR tensor-core block value types */
+typedef enum { CUSPMM_BLK_BF16 = 0, CUSPMM_BLK_FP16 = 1 } cuspmmBlockType;
+
+/* ------------------------------------------------------------------ misc ---- */
+int cuspmm_version(void);
+const char *cuspmm_last_error(void);
+/* Number of launches of THIS library's kernels issued by the calling thread since
+ * the last cuspmm_reset_launch_count() (bench.py's gpu_launches). */
+unsigned long long cuspmm_launch_count(void);
+void cuspmm_reset_launch_count(void);
+int cuspmm_device_count(int *count);
+int cuspmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
+                       size_t *l2_bytes, size_t *total_mem_bytes);
+
+/* ------------------------------------------------------------------- CSR ---- */
+/* Replaces spmmCSRWrapper1..4 / spmmCSRK1..4 (include/engine/engine_csr.hpp:15-25,
+ * src/spmm/csr/spmm_csr_k{1,2,3,4}.cu).  Variants (Engine<CSR>::runKernel numbers):
+ *   0  auto (selector: DESIGN.md "kernel selection")
+ *   1  row-split, warp per row, 128-bit B loads, nnz-balanced row ranges
+ *   2  vector-per-row: sub-warp per row for narrow N / short rows
+ *   3  staged: row panel x K-chunks, B tiles staged in shared memory by TMA bulk copies
+ *   4  scalar generic (any N, any alignment) */
+#define CUSPMM_CSR_NUM_VARIANTS 4
+int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
+                    uint32_t M, uint32_t K, uint32_t nnz,
+                    const float *B_dev, uint32_t N, size_t ldb,
+                    float *C_dev, size_t ldc, int variant, void *stream);
+
+/* ------------------------------------------------------------------- COO ---- */
+/* Replaces spmmCOOWrapper1 / spmmCOOK1 (include/engine/engine_coo.hpp:14-15,
+ * src/spmm/coo/spmm_coo_k1.cu).  Entries must be sorted by (row, col) as the
+ * reference's converter writes them (convert_mtx.py:181-185).  Variants:
+ *   0 auto, 1 row-aligned nnz split (no atomics, no workspace),
+ *   2 COO->CSR row pointers on device, then the staged CSR kernel
+ *     (needs (M+1)*4 bytes of workspace). */
+#define CUSPMM_COO_NUM_VARIANTS 2
+size_t cuspmm_spmm_coo_workspace(uint32_t M, uint32_t nnz, uint32_t N, int variant);
+int cuspmm_spmm_coo(const uint32_t *rowIdxs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
+                    uint32_t M, uint32_t K, uint32_t nnz,
+                    const float *B_dev, uint32_t N, size_t ldb,
+                    float *C_dev, size_t ldc, int variant,
+                    void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------- ELL ---- */
+/* Sliced ELL (the engine's native ELL layout): slices of `sliceH` (=32) rows, slice
+ * s is W_s slots wide, slot-major: entry j of row s*32+i at slicePtrs[s] + j*32 + i;
+ * padding colIdx 0xFFFFFFFF / value 0.  Replaces spmmELLWrapper1/2 / spmmELLK1/2
+ * (include/engine/engine_ell.hpp:15-19, src/spmm/ell/spmm_ell_k{1,2}.cu). */
+#define CUSPMM_ELL_NUM_VARIANTS 1
+int cuspmm_spmm_sell(const uint32_t *slicePtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
+                     uint32_t M, uint32_t K, uint32_t sliceH,
+                     const float *B_dev, uint32_t N, size_t ldb,
+                     float *C_dev, size_t ldc, int variant, void *stream);
+
+/* The reference's column-ELL storage (include/formats/sparse_ell.hpp:12-37:
+ * rowIdxs/vals are [K x maxColNnz], padding row -1) -> CSR, on the device: a stable
+ * radix sort of the slots by row index.  nnz is the count from the ELL header
+ * (SparseMatrixELL::numNonZero); the call fails with CUSPMM_ERR_INVALID if the
+ * number of non-padding slots differs.  Outputs: rowPtrs_dev[M+1], colIdxs_dev[nnz],
+ * vals_dev[nnz] in (row, col) order.  Temporaries come from the stream-ordered
+ * allocator (cudaMallocAsync); the call synchronises the stream. */
+int cuspmm_colell_to_csr(const uint32_t *ellRowIdxs_dev, const float *ellVals_dev,
+                         uint32_t M, uint32_t K, uint32_t maxColNnz, uint32_t nnz,
+                         uint32_t *rowPtrs_dev, uint32_t *colIdxs_dev, float *vals_dev, void *stream);
+
+/* CSR -> sliced ELL on the device (north_star (b)).  _count fills
+ * slicePtrs_dev[numSlices+1] (numSlices = ceil(M/32)) and returns the total slot
+ * count through *slots_host (synchronises); _fill writes padded colIdxs/vals. */
+int cuspmm_csr_to_sell_count(const uint32_t *rowPtrs_dev, uint32_t M, uint32_t sliceH,
+                             uint32_t *slicePtrs_dev, uint32_t *slots_host, void *stream);
+int cuspmm_csr_to_sell_fill(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
+                            uint32_t M, uint32_t sliceH, const uint32_t *slicePtrs_dev,
+                            uint32_t *sellCols_dev, float *sellVals_dev, void *stream);
+
+/* ------------------------------------------------------------------- BSR ---- */
+/* fp32 blocks, any block shape; bit-for-bit the summation order of spmmBSRCpu.
+ * Replaces spmmBSRWrapper1 / spmmBSRK1 (include/engine/engine_bsr.hpp:15-16,
+ * src/spmm/bsr/spmm_bsr_k1.cu).  M = numBlockRows * br. */
+#define CUSPMM_BSR_NUM_VARIANTS 3 /* 1 fp32 SIMT, 2 bf16 tcgen05, 3 fp16 tcgen05 */
+int cuspmm_spmm_bsr_f32(const uint32_t *blockRowPtrs_dev, const uint32_t *blockColIdxs_dev,
+                        const float *blocks_dev, uint32_t numBlockRows, uint32_t br, uint32_t bc,
+                        uint32_t K, const float *B_dev, uint32_t N, size_t ldb,
+                        float *C_dev, size_t ldc, void *stream);
+
+/* CSR -> BSR on the device (the reference leaves SparseMatrixBSR::fromDense
+ * unimplemented, src/formats/sparse_bsr.cu:259; offline it is scipy tobsr).
+ * M and K are zero-padded up to multiples of br / bc.  _count fills
+ * blockRowPtrs_dev[ceil(M/br)+1] and returns numBlocks (synchronises); _fill writes
+ * ascending blockColIdxs and zero-filled row-major fp32 blocks.  Both sort the
+ * (blockRow, blockCol) keys of the non-zeros with a device radix sort; temporaries
+ * come from the stream-ordered allocator. */
+int cuspmm_csr_to_bsr_count(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev,
+                            uint32_t M, uint32_t K, uint32_t nnz, uint32_t br, uint32_t bc,
+                            uint32_t *blockRowPtrs_dev, uint32_t *numBlocks_host, void *stream);
+int cuspmm_csr_to_bsr_fill(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
+                           uint32_t M, uint32_t K, uint32_t nnz, uint32_t br, uint32_t bc,
+                           uint32_t numBlocks, uint32_t *blockColIdxs_dev, float *blocks_dev, void *stream);
+
+/* Tensor-core BSR (north_star: tcgen05 MMA, TMEM accumulators, TMA-fed, fp32
+ * accumulate).  Square blocks of 16 or 32.  The plan owns device copies of the
+ * blocks in bf16/fp16 laid out as UMMA core matrices and a scratch for the
+ * converted B; `prepare_B` casts + re-tiles B (K x N fp32) once per B, `run`
+ * multiplies.  Results equal the fp32 product of the ROUNDED operands up to fp32
+ * accumulation order (tolerances: DESIGN.md "parity"). */
+typedef struct cuspmmBsrTcPlan_s *cuspmmBsrTcPlan;
+int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *plan,
+                              const uint32_t *blockRowPtrs_dev, const uint32_t *blockColIdxs_dev,
+                              const float *blocks_dev, uint32_t numBlockRows, uint32_t numBlocks,
+                              uint32_t blockSize, uint32_t K, uint32_t maxN,
+                              cuspmmBlockType type, void *stream);
+int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan plan, const float *B_dev, uint32_t N, size_t ldb, void *stream);
+int cuspmm_bsr_tc_run(cuspmmBsrTcPlan plan, float *C_dev, size_t ldc, void *stream);
+int cuspmm_bsr_tc_plan_destroy(cuspmmBsrTcPlan plan);
+
+/* --------------------------------------------------------- partitioning ---- */
+/* nnz-balanced contiguous row panels (north_star (b)/(c)): splits_host[0] = 0,
+ * splits_host[parts] = M, splits_host[g] = first row r with rowPtrs[r] >= g*nnz/parts.
+ * Runs a device binary search on rowPtrs and synchronises the stream. */
+int cuspmm_partition_rows_by_nnz(const uint32_t *rowPtrs_dev, uint32_t M, uint32_t nnz,
+                                 uint32_t parts, uint32_t *splits_host, void *stream);
+/* COO -> CSR row pointers on the device (entries sorted by row). */
+int cuspmm_coo_to_csr_rowptrs(const uint32_t *rowIdxs_dev, uint32_t M, uint32_t nnz,
+                              uint32_t *rowPtrs_dev, void *stream);
+
+/* ------------------------------------------------- host-buffer entry points ---- */
+/* What runEngine + spmm<FMT>Wrapper<k> do end to end (src/engine/engine.cpp:20-44,
+ * src/spmm/csr/spmm_csr_k3.cu:59-105): operands in HOST memory, H2D, kernel, D2H of
+ * C.  Row panels are pipelined over two streams so the copies overlap the kernel.
+ * Host buffers should be pinned (cudaHostAlloc / cuspmm_host_alloc) for the copies
+ * to be asynchronous.  Synchronises before returning.  `device_ms` (optional)
+ * receives the device time of the whole pipeline measured with CUDA events. */
+int cuspmm_spmm_csr_host(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                         uint32_t M, uint32_t K, uint32_t nnz,
+                         const float *B, uint32_t N, float *C, int variant, float *device_ms);
+int cuspmm_host_alloc(void **ptr, size_t bytes); /* pinned, cf. cudaMallocHost in src/formats/dense.cu:244 */
+int cuspmm_host_free(void *ptr);
+
+/* ------------------------------------------------------ multi-GPU engine ---- */
+/* Row-panel data parallelism over `ngpus` devices of one node (north_star (c);
+ * the reference is single-device, src/main.cu:176).  create(): A (HOST CSR) is split
+ * into nnz-balanced row panels, panel g is uploaded to device devices[g];
+ * set_B(): B (HOST) is uploaded to device 0 and replicated to the peers over
+ * NVLink (cudaMemcpyPeerAsync);  run(): every device multiplies its panel on its
+ * own stream; with gather != 0 each device's kernel writes its C rows straight
+ * into device 0's C through peer memory (no separate collective), otherwise C
+ * stays sharded.  Device time = max over devices, CUDA events.  */
+typedef struct cuspmmMgpuPlan_s *cuspmmMgpuPlan;
+int cuspmm_mgpu_create_csr(cuspmmMgpuPlan *plan, int ngpus, const int *devices,
+                           const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                           uint32_t M, uint32_t K, uint32_t nnz, uint32_t maxN);
+int cuspmm_mgpu_set_B(cuspmmMgpuPlan plan, const float *B, uint32_t N);
+int cuspmm_mgpu_run(cuspmmMgpuPlan plan, int variant, int gather, int iters, float *max_device_ms);
+int cuspmm_mgpu_get_splits(cuspmmMgpuPlan plan, uint32_t *splits /* ngpus+1 */);
+int cuspmm_mgpu_get_C(cuspmmMgpuPlan plan, float *C /* host, M x N */);
+int cuspmm_mgpu_destroy(cuspmmMgpuPlan plan);
+
+/* ------------------------------------------------------ vendor baseline ---- */
+/* cusparseSpMM, fp32 compute, row-major B and C, alpha 1 beta 0: the reference's
+ * cusparseTest (src/engine/cusparse.cu:10-57) with its algorithm choices
+ * (CSR_ALG2: sparse_csr.cu:183-185, COO_ALG4: sparse_coo.cu:98-100), timed with
+ * CUDA events over `iters` launches after `warmup`; handle, descriptors, buffer and
+ * cusparseSpMM_preprocess are outside the timed region.  fmt: 0 CSR, 1 COO.
+ * alg: 0 = the reference's choice, otherwise a cusparseSpMMAlg_t value. */
+int cuspmm_cusparse_spmm(int fmt, const uint32_t *rowOrPtr_dev, const uint32_t *colIdxs_dev,
+                         const float *vals_dev, uint32_t M, uint32_t K, uint32_t nnz,
+                         const float *B_dev, uint32_t N, float *C_dev,
+                         int alg, int warmup, int iters, float *avg_ms, float *min_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUSPMM_B200_H */
