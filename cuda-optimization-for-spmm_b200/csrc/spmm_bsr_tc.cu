@@ -1,0 +1,355 @@
+// spmm_bsr_tc.cu -- tensor-core BSR SpMM for sm_100a: tcgen05.mma, accumulators in TMEM,
+// operands fed by TMA bulk copies, fp32 accumulate (north_star: "BSR: the only path treated
+// as a dense contraction").  Replaces spmmBSRK1 (src/spmm/bsr/spmm_bsr_k1.cu) for 16x16 and
+// 32x32 blocks stored as bf16 / fp16.
+//
+// Mapping: UMMA-M is 128, far larger than a block, so the kernel
+// computes C^T tiles:   D[128 n  x  bs rows] += B^T[128 n  x  16 k] * A_blk^T[16 k  x  bs rows]
+//   MMA "A" operand = 128 columns of B for 16 consecutive k            (M = 128, K = 16)
+//   MMA "B" operand = 16 k-columns of the sparse block, all bs rows    (N = bs,  K = 16)
+//   D (TMEM)        = lane n, column i  ==  C[blockRow*bs + i][n]      (fp32)
+// One CTA owns one block row and up to 512 columns (4 D tiles = 4*bs TMEM columns) and walks
+// the block row's blocks through a 4-stage smem ring.
+//
+// Operand layout.  Both operands are K-major with NO swizzle, i.e. UMMA "core matrices" of
+// 8 rows x 16 bytes stored contiguously (128 B): element (row, k) lives at
+//     [k / 8][row][k % 8]          ("K-blocked")
+// so that  SBO (next 8 rows) = 128 B  and  LBO (next 8 k) = rows * 16 B.
+// The plan pre-tiles the blocks that way once; prepare_B() casts B to bf16/fp16 and re-tiles
+// it to Bq[Kpad/8][Npad][8] once per B.  With that layout every stage is filled by plain 1-D
+// TMA bulk copies (cp.async.bulk.shared.global, UBLKCP): one for the block (bs*bs*2 B) and one
+// for the bs x Ntile slab of Bq (contiguous when the CTA covers whole rows of Bq).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (tcgen05.ld 32x32b -> coalesced 128-byte row stores).
+#include "common.cuh"
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace cuspmm_b200 {
+namespace bsrtc {
+
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr int kMaxTileN = 512;     // columns of C per CTA (4 UMMA M-tiles)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1u << 24)) __trap();   // fail loudly instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {   // arrives on bar when all prior MMAs are done
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1, [61,64) layout = 0.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6),
+// a/b format (F16 = 0, BF16 = 1) @ [7,10) / [10,13), both K-major, N>>3 @ [17,23), M>>4 @ [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int BS>
+struct Smem {
+    static constexpr uint32_t kBlockBytes = BS * BS * 2;
+    static constexpr uint32_t kSlabBytes = BS * kMaxTileN * 2;          // bs k-rows x 512 n x 16 bit
+    static constexpr uint32_t kStageBytes = kSlabBytes + kBlockBytes;
+    static constexpr uint32_t kTotal = kStages * kStageBytes + (2 * kStages + 1) * 8 + 16 + 128;
+};
+
+// grid = (numBlockRows, ceil(Npad / 512)); FMT: 1 = bf16, 0 = fp16
+template <int BS, int FMT>
+__global__ void __launch_bounds__(kThreads)
+bsr_tc_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *__restrict__ blockColIdxs,
+              const uint16_t *__restrict__ blocksQ,   // [numBlocks][BS/8][BS][8]
+              const uint16_t *__restrict__ Bq,        // [Kpad/8][Npad][8]
+              uint32_t Npad, uint32_t N, float *__restrict__ C, size_t ldc) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using S = Smem<BS>;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * S::kStageBytes);
+    uint64_t *empty = full + kStages;
+    uint64_t *accum_full = empty + kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t R = blockIdx.x;
+    const uint32_t n0 = blockIdx.y * kMaxTileN;
+    const uint32_t ntile = min((uint32_t)kMaxTileN, Npad - n0);      // multiple of 128
+    const uint32_t tiles = ntile / 128;
+    const uint32_t bstart = __ldg(blockRowPtrs + R), bend = __ldg(blockRowPtrs + R + 1);
+    const uint32_t nblk = bend - bstart;
+    constexpr uint32_t kTmemCols = 4 * BS;                            // 64 or 128: power of two >= 32
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            for (uint32_t i = 0; i < nblk; ++i) {
+                const uint32_t s = i % kStages, it = i / kStages;
+                if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+                unsigned char *slab = smem + s * S::kStageBytes;
+                unsigned char *blk = slab + S::kSlabBytes;
+                const uint32_t b = bstart + i;
+                const uint32_t bcol = __ldg(blockColIdxs + b);
+                const uint32_t slabBytes = (BS / 8) * ntile * 16;
+                mbar_expect_tx(full + s, slabBytes + S::kBlockBytes);
+                bulk_g2s(blk, blocksQ + (size_t)b * BS * BS, S::kBlockBytes, full + s);
+                const uint16_t *src = Bq + ((size_t)bcol * (BS / 8) * Npad + n0) * 8;
+                if (ntile == Npad) {
+                    bulk_g2s(slab, src, slabBytes, full + s);             // BS/8 k-groups are contiguous
+                } else {
+#pragma unroll
+                    for (int kb = 0; kb < BS / 8; ++kb)
+                        bulk_g2s(slab + (size_t)kb * ntile * 16, src + (size_t)kb * Npad * 8, ntile * 16, full + s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT, 128, BS);
+            for (uint32_t i = 0; i < nblk; ++i) {
+                const uint32_t s = i % kStages, it = i / kStages;
+                mbar_wait(full + s, it & 1);
+                tc_fence_after();
+                const uint32_t slab = smem_u32(smem + s * S::kStageBytes);
+                const uint32_t blk = slab + S::kSlabBytes;
+#pragma unroll
+                for (int ks = 0; ks < BS / 16; ++ks) {
+                    // B operand: block k-groups 2ks, 2ks+1: [kb][BS rows][8]  -> LBO = BS*16, SBO = 128
+                    const uint64_t bdesc = make_desc(blk + ks * 2 * BS * 16, BS * 16, 128);
+                    for (uint32_t t = 0; t < tiles; ++t) {
+                        // A operand: slab k-groups 2ks, 2ks+1, rows n = 128t .. 128t+127 -> LBO = ntile*16, SBO = 128
+                        const uint64_t adesc = make_desc(slab + ks * 2 * ntile * 16 + t * 128 * 16, ntile * 16, 128);
+                        umma_f16(tmem_base + t * BS, adesc, bdesc, idesc, (i | ks) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty + s);          // stage s may be refilled once these MMAs have read it
+            }
+            umma_commit(accum_full);             // all accumulators final
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const uint32_t q = warp & 3;             // TMEM lane quarter this warp may access
+        if (nblk > 0) {
+            mbar_wait(accum_full, 0);
+            tc_fence_after();
+        }
+        for (uint32_t t = 0; t < tiles; ++t) {
+            uint32_t v[BS];
+            if (nblk > 0) {
+                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + t * BS;
+                if constexpr (BS == 16) {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(taddr));
+                } else {
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                 : "r"(taddr));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < BS; ++j) v[j] = 0u;       // a block row without blocks is a zero row of C
+            }
+            const uint32_t n = n0 + t * 128 + q * 32 + lane;
+            if (n < N) {
+                float *cp = C + (size_t)R * BS * ldc + n;
+#pragma unroll
+                for (int j = 0; j < BS; ++j) __stcs(cp + (size_t)j * ldc, __uint_as_float(v[j]));   // 32 lanes = one 128-byte line
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ operand preparation
+template <typename T> __device__ __forceinline__ uint16_t cvt16(float x);
+template <> __device__ __forceinline__ uint16_t cvt16<__nv_bfloat16>(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
+template <> __device__ __forceinline__ uint16_t cvt16<__half>(float x) { return __half_as_ushort(__float2half_rn(x)); }
+
+// blocks fp32 [nb][bs][bs] (row-major, the reference's layout) -> [nb][bs/8][bs][8] 16-bit
+template <typename T>
+__global__ void tile_blocks_kernel(const float *__restrict__ blocks, uint64_t total, uint32_t bs, uint16_t *__restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over output elements
+    if (idx >= total) return;
+    const uint32_t per = bs * bs;
+    const uint64_t b = idx / per;
+    const uint32_t o = (uint32_t)(idx % per);
+    const uint32_t e = o % 8, i = (o / 8) % bs, kb = o / (8 * bs);
+    out[idx] = cvt16<T>(blocks[b * per + (uint64_t)i * bs + kb * 8 + e]);
+}
+
+// B fp32 [K][N] (ldb) -> Bq[Kpad/8][Npad][8] 16-bit, zero padded; one thread per (kb, n): 8 coalesced reads, one 16-byte write
+template <typename T>
+__global__ void tile_B_kernel(const float *__restrict__ B, uint32_t K, uint32_t N, size_t ldb, uint32_t Kpad8, uint32_t Npad,
+                              uint4 *__restrict__ out) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)Kpad8 * Npad) return;
+    const uint32_t n = (uint32_t)(idx % Npad), kb = (uint32_t)(idx / Npad);
+    uint16_t h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t k = kb * 8 + e;
+        h[e] = (k < K && n < N) ? cvt16<T>(__ldg(B + (size_t)k * ldb + n)) : (uint16_t)0;
+    }
+    uint4 v;
+    v.x = h[0] | ((uint32_t)h[1] << 16); v.y = h[2] | ((uint32_t)h[3] << 16);
+    v.z = h[4] | ((uint32_t)h[5] << 16); v.w = h[6] | ((uint32_t)h[7] << 16);
+    out[idx] = v;
+}
+
+} // namespace bsrtc
+} // namespace cuspmm_b200
+
+using namespace cuspmm_b200;
+
+struct cuspmmBsrTcPlan_s {
+    const uint32_t *blockRowPtrs = nullptr, *blockColIdxs = nullptr;   // borrowed (caller keeps them alive)
+    uint16_t *blocksQ = nullptr, *Bq = nullptr;
+    uint32_t numBlockRows = 0, numBlocks = 0, bs = 0, K = 0, Kpad = 0, maxN = 0, maxNpad = 0, N = 0, Npad = 0;
+    int type = 0;
+    int dev = 0;
+};
+
+extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs,
+                                         const float *blocks, uint32_t numBlockRows, uint32_t numBlocks, uint32_t bs,
+                                         uint32_t K, uint32_t maxN, cuspmmBlockType type, void *stream) {
+    CUSPMM_REQUIRE(out && blockRowPtrs && maxN >= 1, "bad arguments");
+    if (bs != 16 && bs != 32)
+        return set_error(CUSPMM_ERR_UNSUPPORTED, "tensor-core BSR supports 16x16 and 32x32 blocks (got %u)", bs);
+    CUSPMM_REQUIRE(type == CUSPMM_BLK_BF16 || type == CUSPMM_BLK_FP16, "unknown block type %d", (int)type);
+    cudaStream_t st = as_stream(stream);
+    auto *p = new cuspmmBsrTcPlan_s();
+    p->blockRowPtrs = blockRowPtrs; p->blockColIdxs = blockColIdxs;
+    p->numBlockRows = numBlockRows; p->numBlocks = numBlocks; p->bs = bs; p->K = K; p->type = (int)type;
+    p->Kpad = (K + bs - 1) / bs * bs;
+    p->maxN = maxN; p->maxNpad = (maxN + 127) / 128 * 128;
+    cudaGetDevice(&p->dev);
+    const uint64_t total = (uint64_t)numBlocks * bs * bs;
+    if (cudaMalloc(&p->blocksQ, (total ? total : 1) * 2) != cudaSuccess ||
+        cudaMalloc(&p->Bq, (size_t)p->Kpad * p->maxNpad * 2) != cudaSuccess) {
+        cudaFree(p->blocksQ); cudaFree(p->Bq); delete p;
+        return set_error(CUSPMM_ERR_CUDA, "cudaMalloc of the tensor-core BSR plan failed");
+    }
+    if (total) {
+        const unsigned grid = (unsigned)((total + 255) / 256);
+        if (type == CUSPMM_BLK_BF16) bsrtc::tile_blocks_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(blocks, total, bs, p->blocksQ);
+        else bsrtc::tile_blocks_kernel<__half><<<grid, 256, 0, st>>>(blocks, total, bs, p->blocksQ);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cudaFree(p->blocksQ); cudaFree(p->Bq); delete p;
+            return set_error(CUSPMM_ERR_CUDA, "launch of tile_blocks_kernel failed: %s", cudaGetErrorString(e));
+        }
+        count_launch();
+    }
+    *out = p;
+    return CUSPMM_OK;
+}
+
+extern "C" int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan p, const float *B, uint32_t N, size_t ldb, void *stream) {
+    CUSPMM_REQUIRE(p && B && N >= 1 && N <= p->maxN && ldb >= N, "bad arguments (N=%u, maxN=%u)", N, p ? p->maxN : 0);
+    p->N = N;
+    p->Npad = (N + 127) / 128 * 128;
+    const uint64_t total = (uint64_t)(p->Kpad / 8) * p->Npad;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (p->type == CUSPMM_BLK_BF16)
+        bsrtc::tile_B_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>(B, p->K, N, ldb, p->Kpad / 8, p->Npad, reinterpret_cast<uint4 *>(p->Bq));
+    else
+        bsrtc::tile_B_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(B, p->K, N, ldb, p->Kpad / 8, p->Npad, reinterpret_cast<uint4 *>(p->Bq));
+    CUSPMM_LAUNCH_CHECK("tile_B_kernel");
+    return CUSPMM_OK;
+}
+
+template <int BS, int FMT>
+static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
+    auto kern = bsrtc::bsr_tc_kernel<BS, FMT>;
+    static bool attr_done[64] = {};
+    if (!attr_done[p->dev & 63]) {
+        CUSPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsrtc::Smem<BS>::kTotal));
+        attr_done[p->dev & 63] = true;
+    }
+    dim3 grid(p->numBlockRows, (p->Npad + bsrtc::kMaxTileN - 1) / bsrtc::kMaxTileN);
+    kern<<<grid, bsrtc::kThreads, bsrtc::Smem<BS>::kTotal, st>>>(p->blockRowPtrs, p->blockColIdxs, p->blocksQ, p->Bq, p->Npad, p->N, C, ldc);
+    CUSPMM_LAUNCH_CHECK("bsr_tc_kernel");
+    return CUSPMM_OK;
+}
+
+extern "C" int cuspmm_bsr_tc_run(cuspmmBsrTcPlan p, float *C, size_t ldc, void *stream) {
+    CUSPMM_REQUIRE(p && C && p->N >= 1, "prepare_B must be called before run");
+    CUSPMM_REQUIRE(ldc >= p->N, "ldc must be >= N");
+    if (p->numBlockRows == 0) return CUSPMM_OK;
+    cudaStream_t st = as_stream(stream);
+    if (p->bs == 16) return p->type == CUSPMM_BLK_BF16 ? launch_tc<16, 1>(p, C, ldc, st) : launch_tc<16, 0>(p, C, ldc, st);
+    return p->type == CUSPMM_BLK_BF16 ? launch_tc<32, 1>(p, C, ldc, st) : launch_tc<32, 0>(p, C, ldc, st);
+}
+
+extern "C" int cuspmm_bsr_tc_plan_destroy(cuspmmBsrTcPlan p) {
+    if (!p) return CUSPMM_OK;
+    cudaFree(p->blocksQ);
+    cudaFree(p->Bq);
+    delete p;
+    return CUSPMM_OK;
+}
