@@ -15,6 +15,8 @@
 //   variant 4  csr_rowsplit_scalar any N / ldb / alignment (N = 21 in data/small_210)
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace cuspmm_b200 {
 
 // =============================================================== variant 1 / 4
@@ -239,7 +241,10 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + CFG::kStageBytes * STAGES);
     uint64_t *empty = full + STAGES;
 
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    // warp index through a shuffle: tells the compiler it is warp-uniform, so everything derived
+    // from it (row numbers, cursors, trip counts) lives in uniform registers and branches on it
+    // need no divergence handling around the shuffles below
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = lane_id();
     const uint32_t col0 = blockIdx.y * NT;                 // column tile (N % NT == 0 checked on host)
     const uint32_t row0 = blockIdx.x * rpc;
     const uint32_t rowEnd = min(M, row0 + rpc);
@@ -253,42 +258,53 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
 
     if (warp == NW) {
         // ------------------------------------------------------------ producer
-        if (lane == 0) {
-            for (uint32_t ch = 0; ch < nchunks; ++ch) {
-                const uint32_t s = ch % STAGES, it = ch / STAGES;
-                if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
-                const uint32_t k0 = ch * KC;
-                const uint32_t rows = min((uint32_t)KC, K - k0);
-                float *dst = tiles + (size_t)s * KC * NT;
-                mbar_expect_tx(full + s, rows * NT * (uint32_t)sizeof(float));
-                if ((size_t)NT == ldb) {       // tile rows are contiguous in B: one bulk copy
+        // lane 0 arms the barrier; when the tile rows are not contiguous in B (NT < ldb) all 32
+        // lanes issue row copies in parallel (one thread issuing KC copies would be the bottleneck)
+        for (uint32_t ch = 0; ch < nchunks; ++ch) {
+            const uint32_t s = ch % STAGES, it = ch / STAGES;
+            if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+            const uint32_t k0 = ch * KC;
+            const uint32_t rows = min((uint32_t)KC, K - k0);
+            float *dst = tiles + (size_t)s * KC * NT;
+            if (lane == 0) mbar_expect_tx(full + s, rows * NT * (uint32_t)sizeof(float));
+            __syncwarp();
+            if ((size_t)NT == ldb) {       // tile rows are contiguous in B: one bulk copy
+                if (lane == 0)
                     bulk_g2s(dst, B + (size_t)k0 * ldb + col0, rows * NT * (uint32_t)sizeof(float), full + s);
-                } else {
-                    for (uint32_t i = 0; i < rows; ++i)
-                        bulk_g2s(dst + (size_t)i * NT, B + (size_t)(k0 + i) * ldb + col0,
-                                 NT * (uint32_t)sizeof(float), full + s);
-                }
+            } else {
+                for (uint32_t i = lane; i < rows; i += 32)
+                    bulk_g2s(dst + (size_t)i * NT, B + (size_t)(k0 + i) * ldb + col0,
+                             NT * (uint32_t)sizeof(float), full + s);
             }
         }
         return;
     }
 
     // ---------------------------------------------------------------- consumers
-    uint32_t pos[RW], end[RW], bufbase[RW], bcol[RW];
+    // Per row: a 32-entry register window of (col, val) (lane l holds entry wbase + l; lanes past
+    // the row end hold kPad), wj = entries of the window already consumed.
+    uint32_t wbase[RW], wj[RW], end[RW], bcol[RW];
     float bval[RW];
     float4 acc[RW][U];
+    auto refill = [&](int i, uint32_t from) {
+        wbase[i] = from;
+        wj[i] = 0;
+        bcol[i] = kPad;
+        bval[i] = 0.f;
+        if (from + lane < end[i]) {
+            bcol[i] = ld_stream(colIdxs + from + lane);
+            bval[i] = ld_stream(vals + from + lane);
+        }
+    };
 #pragma unroll
     for (int i = 0; i < RW; ++i) {
         const uint32_t r = row0 + warp * RW + i;
-        pos[i] = end[i] = 0;
-        if (r < rowEnd) { pos[i] = __ldg(rowPtrs + r); end[i] = __ldg(rowPtrs + r + 1); }
-        bufbase[i] = pos[i];
-        bcol[i] = kPad;
-        bval[i] = 0.f;
-        if (pos[i] + lane < end[i]) {
-            bcol[i] = ld_stream(colIdxs + pos[i] + lane);
-            bval[i] = ld_stream(vals + pos[i] + lane);
-        }
+        uint32_t p0 = 0;
+        end[i] = 0;
+        if (r < rowEnd) { p0 = __ldg(rowPtrs + r); end[i] = __ldg(rowPtrs + r + 1); }
+        p0 = __shfl_sync(0xFFFFFFFFu, p0, 0);
+        end[i] = __shfl_sync(0xFFFFFFFFu, end[i], 0);
+        refill(i, p0);
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[i][u] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -296,29 +312,50 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
     for (uint32_t ch = 0; ch < nchunks; ++ch) {
         const uint32_t s = ch % STAGES, it = ch / STAGES;
         const uint32_t k0 = ch * KC, k1 = k0 + KC;
-        mbar_wait(full + s, it & 1);
-        const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * KC * NT) + lane;
+        // how many window entries of each row fall into this chunk: columns are ascending, so
+        // the lanes with col < k1 form a prefix; drop the wj already-consumed ones.
+        uint32_t nn[RW], maxn = 0;
 #pragma unroll
         for (int i = 0; i < RW; ++i) {
-            while (pos[i] < end[i]) {
-                uint32_t j = pos[i] - bufbase[i];
-                if (j == 32) {                       // refill the 32-entry register window
-                    bufbase[i] = pos[i];
-                    bcol[i] = kPad;
-                    bval[i] = 0.f;
-                    if (pos[i] + lane < end[i]) {
-                        bcol[i] = ld_stream(colIdxs + pos[i] + lane);
-                        bval[i] = ld_stream(vals + pos[i] + lane);
-                    }
-                    j = 0;
-                }
-                const uint32_t c = __shfl_sync(0xFFFFFFFFu, bcol[i], j);
-                if (c >= k1) break;
-                const float v = __shfl_sync(0xFFFFFFFFu, bval[i], j);
-                const float4 *brow = tile + (size_t)(c - k0) * (NT / 4);
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, bcol[i] < k1);
+            nn[i] = wj[i] < 32 ? __popc(m >> wj[i]) : 0;
+            maxn = max(maxn, nn[i]);
+        }
+        mbar_wait(full + s, it & 1);
+        const float4 *tile = reinterpret_cast<const float4 *>(tiles + (size_t)s * KC * NT) + lane;
+        // t-th entry of every row in flight together: RW independent shuffle -> LDS -> FMA chains
+        for (uint32_t t = 0; t < maxn; ++t) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) fma4(acc[i][u], v, brow[u * 32]);
-                ++pos[i];
+            for (int i = 0; i < RW; ++i) {
+                if (t < nn[i]) {
+                    const uint32_t c = __shfl_sync(0xFFFFFFFFu, bcol[i], wj[i] + t);
+                    const float v = __shfl_sync(0xFFFFFFFFu, bval[i], wj[i] + t);
+                    const float4 *brow = tile + (size_t)(c - k0) * (NT / 4);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) fma4(acc[i][u], v, brow[u * 32]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RW; ++i) {
+            wj[i] += nn[i];
+            // window used up while the row may still have entries inside this chunk (rare: once
+            // per 32 non-zeros of a row): refill and finish the chunk entry by entry
+            if (wj[i] == 32 && wbase[i] + 32 < end[i]) {
+                refill(i, wbase[i] + 32);
+                while (true) {
+                    if (wj[i] == 32) {
+                        if (wbase[i] + 32 >= end[i]) break;
+                        refill(i, wbase[i] + 32);
+                    }
+                    const uint32_t c = __shfl_sync(0xFFFFFFFFu, bcol[i], wj[i]);
+                    if (c >= k1) break;                  // also ends at the row end (kPad)
+                    const float v = __shfl_sync(0xFFFFFFFFu, bval[i], wj[i]);
+                    const float4 *brow = tile + (size_t)(c - k0) * (NT / 4);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) fma4(acc[i][u], v, brow[u * 32]);
+                    ++wj[i];
+                }
             }
         }
         __syncwarp();
@@ -429,6 +466,9 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
     case 3: {
         if (!(vok && N % 128 == 0))
             return set_error(CUSPMM_ERR_UNSUPPORTED, "staged CSR kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
+        static const int forceNT = getenv("CUSPMM_STAGED_NT") ? atoi(getenv("CUSPMM_STAGED_NT")) : 0;   // tuning hook
+        if (forceNT == 128) return staged::launch<staged::Cfg<128, 15, 8, 128, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        if (forceNT == 256 && N % 256 == 0) return staged::launch<staged::Cfg<256, 15, 8, 64, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         if (N % 512 == 0) return staged::launch<staged::Cfg<512, 15, 4, 32, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         if (N % 256 == 0) return staged::launch<staged::Cfg<256, 15, 8, 64, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         return staged::launch<staged::Cfg<128, 15, 8, 128, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
