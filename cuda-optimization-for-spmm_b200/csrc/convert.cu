@@ -236,6 +236,19 @@ __global__ void colell_gather_kernel(const uint32_t *__restrict__ sortedIdx, con
     vals[i] = ellVals[slot];
 }
 
+// ------------------------------------------------------------------ dense transpose
+__global__ void __launch_bounds__(256) transpose_kernel(const float *__restrict__ in, uint32_t rows, uint32_t cols,
+                                                        float *__restrict__ out) {
+    __shared__ float tile[32][33];
+    const uint32_t c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (uint32_t j = ty; j < 32; j += 8)
+        if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = in[(size_t)(r0 + j) * cols + c0 + tx];
+    __syncthreads();
+    for (uint32_t j = ty; j < 32; j += 8)
+        if (c0 + j < cols && r0 + tx < rows) out[(size_t)(c0 + j) * rows + r0 + tx] = tile[tx][j];
+}
+
 struct AsyncBuf {   // stream-ordered temporary
     void *p = nullptr;
     cudaStream_t st;
@@ -270,6 +283,15 @@ static int sort_bsr_keys(const uint32_t *rowPtrs, const uint32_t *colIdxs, uint3
 } // namespace cuspmm_b200
 
 using namespace cuspmm_b200;
+
+extern "C" int cuspmm_transpose_f32(const float *in, uint32_t rows, uint32_t cols, float *out, void *stream) {
+    CUSPMM_REQUIRE(in && out, "null pointer");
+    if (!rows || !cols) return CUSPMM_OK;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, rows, cols, out);
+    CUSPMM_LAUNCH_CHECK("transpose_kernel");
+    return CUSPMM_OK;
+}
 
 extern "C" int cuspmm_coo_to_csr_rowptrs(const uint32_t *rowIdxs, uint32_t M, uint32_t nnz, uint32_t *rowPtrs,
                                          void *stream) {

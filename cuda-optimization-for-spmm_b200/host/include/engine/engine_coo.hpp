@@ -1,0 +1,59 @@
+// engine/engine_coo.hpp -- EngineCOO: kernel-number dispatch for the COO path.
+// Same interface as the reference's include/engine/engine_coo.hpp (spmmCOOCpu, spmmCOOWrapper<k>,
+// EngineCOO{MataT, MatbT, SUPPORT_CUSPARSE, fmt, dirPath, seqTime, logSeq, report, runKernel}).
+// Every GPU wrapper multiplies through the C ABI (include/cuspmm_b200.h); there is no CPU fallback.
+#pragma once
+
+#include "commons.hpp"
+#include "engine/cusparse.hpp"
+#include "engine/engine_base.hpp"
+#include "formats/dense.hpp"
+#include "formats/sparse_coo.hpp"
+#include "spmm_cusparse.hpp"
+
+namespace cuspmm {
+
+// kernel 0: the reference's host SpMM (in-process checker)
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmCOOCpu(SparseMatrixCOO<DT, MT> *ma, DenseMatrix<DT, MT> *mb, DenseMatrix<DT, MT> *mc);
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmCOOWrapper1(SparseMatrixCOO<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmCOOWrapper2(SparseMatrixCOO<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+
+template <typename DT, typename MT, typename AccT>
+class EngineCOO : public EngineBase {
+  public:
+    using MataT = SparseMatrixCOO<DT, MT>;
+    using MatbT = DenseMatrix<DT, MT>;
+
+    bool SUPPORT_CUSPARSE = true;
+    std::string fmt;
+    std::string dirPath;
+    double seqTime = 1.f;
+
+    explicit EngineCOO(std::string dirPath) {
+        this->numKernels = 2;
+        this->dirPath = dirPath;
+        this->fmt = "COO";
+    }
+
+    void logSeq(double seq) { this->seqTime = seq; }
+
+    void report(MataT *a, MatbT *b, int num, double pro, double kernel, double epilog, bool correct) {
+        reportTime(this->dirPath, a->numRows, a->numCols, a->numNonZero, this->fmt, b->ordering, num, pro, kernel, epilog, correct);
+    }
+
+    void *runKernel(int num, void *_ma, void *_mb, void *_mc) override {
+        auto ma = reinterpret_cast<MataT *>(_ma);
+        auto mb = reinterpret_cast<MatbT *>(_mb);
+        auto mc = reinterpret_cast<MatbT *>(_mc);
+        if (num == 0) return spmmCOOCpu<DT, MT, AccT>(ma, mb, mc);
+        if (num == 1) return spmmCOOWrapper1<DT, MT, AccT>(ma, mb, mc);
+        if (num == 2) return spmmCOOWrapper2<DT, MT, AccT>(ma, mb, mc);
+        if (num == -1) return spmmCOOWrapper1<DT, MT, AccT>(ma, mb, mc);
+        throw std::runtime_error("Not implemented");
+    }
+};
+
+}  // namespace cuspmm

@@ -162,6 +162,10 @@ int cuspmm_partition_rows_by_nnz(const uint32_t *rowPtrs_dev, uint32_t M, uint32
 int cuspmm_coo_to_csr_rowptrs(const uint32_t *rowIdxs_dev, uint32_t M, uint32_t nnz,
                               uint32_t *rowPtrs_dev, void *stream);
 
+/* Dense transpose on the device: out[c * rows + r] = in[r * cols + c].  Replaces the host
+ * double loop of DenseMatrix::toOrdering (src/formats/dense.cu:140-191). */
+int cuspmm_transpose_f32(const float *in_dev, uint32_t rows, uint32_t cols, float *out_dev, void *stream);
+
 /* ------------------------------------------------- host-buffer entry points ---- */
 /* What runEngine + spmm<FMT>Wrapper<k> do end to end (src/engine/engine.cpp:20-44,
  * src/spmm/csr/spmm_csr_k3.cu:59-105): operands in HOST memory, H2D, kernel, D2H of
