@@ -175,7 +175,7 @@ def main():
     else:
         sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
         alg_bytes = wl.sell_bytes(M, K, N, int(sc.numel()), int(sp.numel()) - 1)
-        step = lambda: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=0, out=Cd)
+        step = lambda: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=args.variant, out=Cd)
 
     def barrier():
         if world > 1:

@@ -37,7 +37,7 @@ def lib():
         L.cuspmm_spmm_coo_workspace.argtypes = [U32, U32, U32, C.c_int]
         L.cuspmm_spmm_csr.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P]
         L.cuspmm_spmm_coo.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P, SZ, P]
-        L.cuspmm_spmm_sell.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P]
+        L.cuspmm_spmm_sell.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P]
         L.cuspmm_spmm_bsr_f32.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, SZ, P, SZ, P]
         L.cuspmm_colell_to_csr.argtypes = [P, P, U32, U32, U32, U32, P, P, P, P]
         L.cuspmm_csr_to_sell_count.argtypes = [P, U32, U32, P, C.POINTER(U32), P]
@@ -130,8 +130,8 @@ def spmm_sell(slicePtrs, colIdxs, vals, M, K, B, variant=0, out=None):
     torch = _torch()
     N = B.shape[1]
     Cm = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=B.device)
-    check(lib().cuspmm_spmm_sell(_ptr(slicePtrs), _ptr(colIdxs), _ptr(vals), M, K, 32, _ptr(B), N, B.stride(0),
-                                 _ptr(Cm), Cm.stride(0), variant, _stream()), "cuspmm_spmm_sell")
+    check(lib().cuspmm_spmm_sell(_ptr(slicePtrs), _ptr(colIdxs), _ptr(vals), M, K, 32, int(colIdxs.numel()), _ptr(B), N,
+                                 B.stride(0), _ptr(Cm), Cm.stride(0), variant, _stream()), f"cuspmm_spmm_sell(variant={variant})")
     return Cm
 
 

@@ -16,6 +16,7 @@ namespace cuspmm_b200 {
 int spmm_csr_dispatch(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, uint32_t,
                       const float *, uint32_t, size_t, float *, size_t, int, cudaStream_t);
 int coo_to_csr_rowptrs(const uint32_t *rowIdxs, uint32_t M, uint32_t nnz, uint32_t *rowPtrs, cudaStream_t st);
+int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok);
 
 // first index i in [from, nnz] whose row is > `row` (i.e. the start of the next row)
 __device__ __forceinline__ uint32_t next_row_start(const uint32_t *__restrict__ rowIdxs, uint32_t nnz,
@@ -155,10 +156,9 @@ static int spmm_coo_dispatch(const uint32_t *rowIdxs, const uint32_t *colIdxs, c
     CUSPMM_REQUIRE(B && C && (nnz == 0 || (rowIdxs && colIdxs && vals)), "null operand pointer");
     const bool vok = (N % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    if (variant == 0) {
-        const double density = (double)nnz / ((double)M * (double)K);
-        const bool staged_ok = vok && (N % 128 == 0) && M >= 1024 && ws && ws_bytes >= (size_t)(M + 1) * 4;
-        variant = (staged_ok && density * 64.0 >= 2.0) ? 2 : 1;
+    if (variant == 0) {   // the CSR selector decides whether the staged kernel pays; it needs row pointers
+        const bool have_ws = ws && ws_bytes >= (size_t)(M + 1) * 4;
+        variant = (have_ws && csr_select_variant(M, K, nnz, N, vok) == 3) ? 2 : 1;
     }
     if (variant == 2) {
         if (ws_bytes < (size_t)(M + 1) * 4 || !ws)

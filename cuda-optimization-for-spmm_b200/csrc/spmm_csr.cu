@@ -226,7 +226,10 @@ struct Cfg {
     static constexpr size_t kSmemBytes = kStageBytes * STAGES + 2 * STAGES * sizeof(uint64_t) + 128;
 };
 
-template <class CFG>
+// SELL = false: CSR (rowPtrs = row pointers, entry idx of a row at colIdxs[idx], idx absolute).
+// SELL = true : sliced ELL (rowPtrs = slicePtrs; entry j of row r at slicePtrs[r/32] + j*32 + r%32,
+//               j in [0, W_slice); padding entries carry colIdx kPad and are never consumed).
+template <class CFG, bool SELL>
 __global__ void __launch_bounds__(CFG::kThreads, 1)
 csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
                   const float *__restrict__ vals, uint32_t M, uint32_t K, uint32_t rpc,
@@ -283,7 +286,7 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
     // ---------------------------------------------------------------- consumers
     // Per row: a 32-entry register window of (col, val) (lane l holds entry wbase + l; lanes past
     // the row end hold kPad), wj = entries of the window already consumed.
-    uint32_t wbase[RW], wj[RW], end[RW], bcol[RW];
+    uint32_t wbase[RW], wj[RW], end[RW], bcol[RW], off[RW];
     float bval[RW];
     float4 acc[RW][U];
     auto refill = [&](int i, uint32_t from) {
@@ -292,8 +295,9 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
         bcol[i] = kPad;
         bval[i] = 0.f;
         if (from + lane < end[i]) {
-            bcol[i] = ld_stream(colIdxs + from + lane);
-            bval[i] = ld_stream(vals + from + lane);
+            const size_t at = SELL ? (size_t)off[i] + (size_t)(from + lane) * 32u : (size_t)(from + lane);
+            bcol[i] = ld_stream(colIdxs + at);
+            bval[i] = ld_stream(vals + at);
         }
     };
 #pragma unroll
@@ -301,9 +305,20 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
         const uint32_t r = row0 + warp * RW + i;
         uint32_t p0 = 0;
         end[i] = 0;
-        if (r < rowEnd) { p0 = __ldg(rowPtrs + r); end[i] = __ldg(rowPtrs + r + 1); }
+        off[i] = 0;
+        if (r < rowEnd) {
+            if constexpr (SELL) {
+                const uint32_t sb = __ldg(rowPtrs + (r >> 5));
+                off[i] = sb + (r & 31u);
+                end[i] = (__ldg(rowPtrs + (r >> 5) + 1) - sb) >> 5;      // slice width in slots
+            } else {
+                p0 = __ldg(rowPtrs + r);
+                end[i] = __ldg(rowPtrs + r + 1);
+            }
+        }
         p0 = __shfl_sync(0xFFFFFFFFu, p0, 0);
         end[i] = __shfl_sync(0xFFFFFFFFu, end[i], 0);
+        off[i] = __shfl_sync(0xFFFFFFFFu, off[i], 0);
         refill(i, p0);
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[i][u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -373,10 +388,10 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
     }
 }
 
-template <class CFG>
+template <class CFG, bool SELL>
 int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
            const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
-    auto kern = csr_staged_kernel<CFG>;
+    auto kern = csr_staged_kernel<CFG, SELL>;
     static bool attr_done[64] = {};
     int dev = 0;
     CUSPMM_CUDA(cudaGetDevice(&dev));
@@ -384,19 +399,33 @@ int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, 
         CUSPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::kSmemBytes));
         attr_done[dev & 63] = true;
     }
-    // whole waves: ctas = waves * SMs (per column tile), rows per CTA = ceil(M / ctas) <= kRows
+    // whole waves: (row panels x column tiles) is made a multiple of the SM count, rows per CTA =
+    // ceil(M / panels) <= kRows
     const uint32_t sms = (uint32_t)sm_count();
-    const uint32_t minCtas = (M + CFG::kRows - 1) / CFG::kRows;
-    const uint32_t waves = (minCtas + sms - 1) / sms;
-    uint32_t ctas = waves * sms;
-    uint32_t rpc = (M + ctas - 1) / ctas;
+    const uint32_t ytiles = N / CFG::kNT;
+    const uint32_t minPanels = (M + CFG::kRows - 1) / CFG::kRows;
+    const uint32_t waves = (minPanels * ytiles + sms - 1) / sms;
+    uint32_t panels = (waves * sms) / ytiles;
+    if (panels < minPanels) panels = minPanels;
+    uint32_t rpc = (M + panels - 1) / panels;
     if (rpc > (uint32_t)CFG::kRows) rpc = CFG::kRows;
     if (rpc == 0) rpc = 1;
-    ctas = (M + rpc - 1) / rpc;
-    dim3 grid(ctas, N / CFG::kNT);
+    panels = (M + rpc - 1) / rpc;
+    dim3 grid(panels, ytiles);
     kern<<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(rowPtrs, colIdxs, vals, M, K, rpc, B, N, ldb, C, ldc);
     CUSPMM_LAUNCH_CHECK("csr_staged_kernel");
     return CUSPMM_OK;
+}
+
+template <bool SELL>
+int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
+                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+    static const int forceNT = getenv("CUSPMM_STAGED_NT") ? atoi(getenv("CUSPMM_STAGED_NT")) : 0;   // tuning hook
+    if (forceNT == 128) return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    if (forceNT == 256 && N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    if (N % 512 == 0) return launch<Cfg<512, 15, 4, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    if (N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
 }
 
 } // namespace staged
@@ -413,6 +442,27 @@ static uint32_t pick_warps(uint32_t M) {
     return (uint32_t)(want < M ? want : (M ? M : 1));
 }
 
+// Kernel selection (DESIGN.md "kernel selection"; measured in profiles/r01_sweep.jsonl):
+//   - no 128-bit loads possible                      -> scalar row-split (4)
+//   - N % 512 == 0, M >= 1024 and each staged B row is re-used by >= 2 rows of a 60-row panel
+//     (density * 60 >= 2)                            -> staged (3): B tiles through shared memory
+//   - narrow N (< 128) or short rows (< 96 nnz/row)  -> sub-warp per row (2)
+//   - otherwise                                      -> warp per row, nnz-balanced (1)
+int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok) {
+    if (!vec_ok) return 4;
+    const double density = (double)nnz / ((double)M * (double)K);
+    const double per_row = (double)nnz / (double)M;
+    if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 2.0) return 3;
+    if (N < 128 || per_row < 96.0) return 2;
+    return 1;
+}
+
+// the staged kernel on a sliced-ELL matrix (spmm_ell.cu)
+int spmm_sell_staged(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
+                     const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+    return staged::launch_by_N<true>(slicePtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+}
+
 int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
                       uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
                       float *C, size_t ldc, int variant, cudaStream_t st) {
@@ -422,15 +472,11 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
     CUSPMM_REQUIRE(rowPtrs && B && C && (nnz == 0 || (colIdxs && vals)), "null operand pointer");
     const bool vok = vec_ok(B, ldb, C, ldc, N);
 
-    if (variant == 0) {   // selector: see DESIGN.md "kernel selection"
-        if (!vok) variant = 4;
-        else if (N < 128) variant = 2;
-        else {
-            const double density = (double)nnz / ((double)M * (double)K);
-            const bool staged_ok = (N % 128 == 0) && M >= 1024;
-            variant = (staged_ok && density * 64.0 >= 2.0) ? 3 : 1;
-        }
-    }
+    if (variant == 0) variant = csr_select_variant(M, K, nnz, N, vok);
+
+    // variants 1 and 2 keep their work decomposition but fall back to 32-bit loads when N, ldb/ldc or
+    // the base pointers rule out 128-bit ones (N = 21 in data/small_210); variant 4 forces that path
+    if ((variant == 1 || variant == 2) && !vok) variant = 4;
 
     const uint32_t warps = pick_warps(M);
     const uint64_t ipw = ((uint64_t)nnz + M + warps - 1) / warps;
@@ -438,7 +484,6 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
 
     switch (variant) {
     case 1: {
-        CUSPMM_REQUIRE(vok, "variant 1 needs N %% 4 == 0 and 16-byte aligned B/C rows (N=%u ldb=%zu ldc=%zu)", N, ldb, ldc);
         if (N > 256) {
             dim3 grid(blocks, (N + 511) / 512);
             csr_rowsplit_vec_kernel<4, 2><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
@@ -453,7 +498,6 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
         return CUSPMM_OK;
     }
     case 2: {
-        CUSPMM_REQUIRE(vok, "variant 2 needs N %% 4 == 0 and 16-byte aligned B/C rows");
         const uint32_t G = N <= 16 ? 4 : (N <= 32 ? 8 : 16);
         const uint32_t rows_per_block = 256 / G;
         dim3 grid((M + rows_per_block - 1) / rows_per_block, (N + 4 * G - 1) / (4 * G));
@@ -466,12 +510,7 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
     case 3: {
         if (!(vok && N % 128 == 0))
             return set_error(CUSPMM_ERR_UNSUPPORTED, "staged CSR kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
-        static const int forceNT = getenv("CUSPMM_STAGED_NT") ? atoi(getenv("CUSPMM_STAGED_NT")) : 0;   // tuning hook
-        if (forceNT == 128) return staged::launch<staged::Cfg<128, 15, 8, 128, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-        if (forceNT == 256 && N % 256 == 0) return staged::launch<staged::Cfg<256, 15, 8, 64, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-        if (N % 512 == 0) return staged::launch<staged::Cfg<512, 15, 4, 32, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-        if (N % 256 == 0) return staged::launch<staged::Cfg<256, 15, 8, 64, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-        return staged::launch<staged::Cfg<128, 15, 8, 128, 3>>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        return staged::launch_by_N<false>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);

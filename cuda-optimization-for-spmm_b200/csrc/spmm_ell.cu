@@ -122,10 +122,13 @@ sell_scalar_kernel(const uint32_t *__restrict__ slicePtrs, const uint32_t *__res
     }
 }
 
+int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok);
+int spmm_sell_staged(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, const float *, uint32_t, size_t,
+                     float *, size_t, cudaStream_t);
+
 static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
-                              uint32_t M, uint32_t K, uint32_t sliceH, const float *B, uint32_t N, size_t ldb,
-                              float *C, size_t ldc, int variant, cudaStream_t st) {
-    (void)K;
+                              uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots, const float *B, uint32_t N,
+                              size_t ldb, float *C, size_t ldc, int variant, cudaStream_t st) {
     CUSPMM_REQUIRE(variant >= 0 && variant <= CUSPMM_ELL_NUM_VARIANTS, "ELL variant %d does not exist", variant);
     CUSPMM_REQUIRE(sliceH == kSliceH, "sliced ELL kernels are built for slices of %d rows (got %u)", kSliceH, sliceH);
     CUSPMM_REQUIRE(ldb >= N && ldc >= N, "ldb/ldc must be >= N");
@@ -134,6 +137,12 @@ static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs
     const uint32_t slices = (M + kSliceH - 1) / kSliceH;
     const bool vok = (N % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    if (variant == 0) variant = (csr_select_variant(M, K, numSlots, N, vok) == 3) ? 2 : 1;   // slots ~ nnz
+    if (variant == 2) {
+        if (!(vok && N % 128 == 0))
+            return set_error(CUSPMM_ERR_UNSUPPORTED, "staged ELL kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
+        return spmm_sell_staged(slicePtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    }
     if (vok) {
         if (N > 256) sell_vec_kernel<4><<<dim3(slices, (N + 511) / 512), 256, 0, st>>>(slicePtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
         else if (N > 128) sell_vec_kernel<2><<<dim3(slices, 1), 256, 0, st>>>(slicePtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
@@ -149,8 +158,8 @@ static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs
 } // namespace cuspmm_b200
 
 extern "C" int cuspmm_spmm_sell(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
-                                uint32_t M, uint32_t K, uint32_t sliceH, const float *B, uint32_t N, size_t ldb,
-                                float *C, size_t ldc, int variant, void *stream) {
-    return cuspmm_b200::spmm_sell_dispatch(slicePtrs, colIdxs, vals, M, K, sliceH, B, N, ldb, C, ldc, variant,
+                                uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots, const float *B, uint32_t N,
+                                size_t ldb, float *C, size_t ldc, int variant, void *stream) {
+    return cuspmm_b200::spmm_sell_dispatch(slicePtrs, colIdxs, vals, M, K, sliceH, numSlots, B, N, ldb, C, ldc, variant,
                                            cuspmm_b200::as_stream(stream));
 }

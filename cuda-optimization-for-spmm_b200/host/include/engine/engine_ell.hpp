@@ -18,6 +18,8 @@ template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLCpu(SparseMatrixELL<DT, MT> *ma, DenseMatrix<DT, MT> *mb, DenseMatrix<DT, MT> *mc);
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper1(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper2(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 
 template <typename DT, typename MT, typename AccT>
 class EngineELL : public EngineBase {
@@ -31,7 +33,7 @@ class EngineELL : public EngineBase {
     double seqTime = 1.f;
 
     explicit EngineELL(std::string dirPath) {
-        this->numKernels = 1;
+        this->numKernels = 2;   // the reference ships Wrapper2 but sets 1 (engine_ell.hpp:32)
         this->dirPath = dirPath;
         this->fmt = "ELL";
     }
@@ -48,6 +50,7 @@ class EngineELL : public EngineBase {
         auto mc = reinterpret_cast<MatbT *>(_mc);
         if (num == 0) return spmmELLCpu<DT, MT, AccT>(ma, mb, mc);
         if (num == 1) return spmmELLWrapper1<DT, MT, AccT>(ma, mb, mc);
+        if (num == 2) return spmmELLWrapper2<DT, MT, AccT>(ma, mb, mc);
         if (num == -1) return spmmELLWrapper1<DT, MT, AccT>(ma, mb, mc);
         throw std::runtime_error("Not implemented");
     }

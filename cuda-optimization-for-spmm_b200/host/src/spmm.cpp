@@ -236,28 +236,38 @@ DenseMatrix<DT, MT> *spmmCOOWrapper2(SparseMatrixCOO<DT, MT> *a, DenseMatrix<DT,
     return cooWrapper<DT, MT, AccT>(2, "coo_rowptr_then_csr_selector", a, b, ref);
 }
 
-// ------------------------------------------------------------------------------- ELL wrapper
+// ------------------------------------------------------------------------------- ELL wrappers
 template <typename DT, typename MT, typename AccT>
-DenseMatrix<DT, MT> *spmmELLWrapper1(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref) {
+static DenseMatrix<DT, MT> *ellWrapper(int k, const char *name, SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b,
+                                       DenseMatrix<DT, MT> *ref) {
     assert(a->onDevice && b->onDevice);
     KernelSpec ks;
-    ks.format = "ELL"; ks.name = "sell32_vec (column-ELL -> sliced ELL on device in prolog)"; ks.kernelNum = 1;
+    ks.format = "ELL"; ks.name = name; ks.kernelNum = k;
     ks.M = a->numRows; ks.K = a->numCols; ks.nnz = a->numNonZero; ks.outRows = a->numRows;
     const double N = b->numCols;
     ks.flops = 2.0 * ks.nnz * N;
     SlicedELL<DT, MT> *s = nullptr;
-    auto prolog = [&]() {
+    auto launch = [&](DenseMatrix<DT, MT> *c) {
+        return cuspmm_spmm_sell(s->slicePtrs, s->colIdxs, s->data, a->numRows, a->numCols, 32, s->numSlots, b->data, b->numCols,
+                                b->numCols, c->data, c->numCols, k, nullptr);
+    };
+    auto prolog = [&]() {      // column-ELL (the reference's storage) -> sliced ELL, on the device
         s = a->toSliced();
         ks.algBytes = 8.0 * s->numSlots + 4.0 * (s->numSlices + 1.0) + 4.0 * ks.K * N + 4.0 * ks.M * N;
-        return true;
-    };
-    auto launch = [&](DenseMatrix<DT, MT> *c) {
-        return cuspmm_spmm_sell(s->slicePtrs, s->colIdxs, s->data, a->numRows, a->numCols, 32, b->data, b->numCols, b->numCols,
-                                c->data, c->numCols, 1, nullptr);
+        DenseMatrix<DT, MT> scratch(a->numRows, b->numCols, true);
+        return launch(&scratch) == CUSPMM_OK;
     };
     auto *c = runWrapper<DT, MT>(ks, b, ref, prolog, launch);
     delete s;
     return c;
+}
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper1(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref) {
+    return ellWrapper<DT, MT, AccT>(1, "sell32_slice_per_cta", a, b, ref);
+}
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper2(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref) {
+    return ellWrapper<DT, MT, AccT>(2, "sell32_staged_tma", a, b, ref);
 }
 
 // ------------------------------------------------------------------------------- BSR wrappers
@@ -327,6 +337,7 @@ template Dn *spmmCSRWrapper4<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper1<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper2<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmELLWrapper1<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);
+template Dn *spmmELLWrapper2<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);
 template Dn *spmmBSRWrapper1<F, U, A>(SparseMatrixBSR<F, U> *, Dn *, Dn *);
 template Dn *spmmBSRWrapper2<F, U, A>(SparseMatrixBSR<F, U> *, Dn *, Dn *);
 template Dn *spmmBSRWrapper3<F, U, A>(SparseMatrixBSR<F, U> *, Dn *, Dn *);

@@ -46,7 +46,7 @@ def main():
             elif fmt == "coo":
                 step = lambda: b.spmm_coo(rows, ci, va, M, K, Bd, variant=v, out=Cd)
             else:
-                step = lambda: b.spmm_sell(sp, sc, sv, M, K, Bd, out=Cd)
+                step = lambda: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=v, out=Cd)
             try:
                 for _ in range(3):
                     step()

@@ -80,12 +80,12 @@ def test_cli_all_formats_on_reference_fixtures(case):
         k, fmt = r["kernelType"], r["format"]
         if fmt == "BSR" and k in ("2", "3"):
             assert r["correct"] == "0"          # 1x1 blocks: the tensor-core variants decline (cf. spmm_csr_k4.cu:97-101)
-        elif fmt == "CSR" and k in ("1", "2", "3") and (n_cols % 4 or (k == "3" and n_cols % 128)):
-            assert r["correct"] == "0"          # vector / staged variants decline N they cannot tile; kernel 4 runs it
+        elif (fmt == "CSR" and k == "3" or fmt == "ELL" and k == "2") and n_cols % 128:
+            assert r["correct"] == "0"          # the staged variant declines N it cannot tile (cf. spmm_csr_k4.cu:97-101)
         else:
             assert r["correct"] == "1", r
         assert r["denseOrdering"] == "ROW_MAJOR"
-    assert [r["kernelType"] for r in by_fmt["ELL"]] == ["0", "1"]
+    assert [r["kernelType"] for r in by_fmt["ELL"]] == ["0", "1", "2"]
 
 
 @pytest.mark.gpu

@@ -55,11 +55,7 @@ def test_fixture_all_formats(b, case, exact):
     denom = orc.absprod_csr(csr, B)
     ref_csr = np.load(os.path.join(d, "ref_csr.npy"))
     rp, ci, va = dev_csr(b, csr)
-    for variant in (0, 1, 2, 4):
-        if variant in (1, 2) and B.shape[1] % 4:
-            with pytest.raises(b.CuspmmError):
-                b.spmm_csr(rp, ci, va, csr.M, csr.K, Bd, variant=variant)
-            continue
+    for variant in (0, 1, 2, 4):      # N = 21 (small_210): variants 1/2 run with 32-bit loads
         check(b.spmm_csr(rp, ci, va, csr.M, csr.K, Bd, variant=variant), ref_csr, denom, exact)
     ref_coo = np.load(os.path.join(d, "ref_coo.npy"))
     for variant in (0, 1):
@@ -108,8 +104,6 @@ def test_csr_coo_ell_random(b, M, K, N, d, skew):
     rp, ci, va = dev_csr(b, a)
     outs = {}
     for variant in (0, 1, 2, 4):
-        if variant in (1, 2) and N % 4:
-            continue
         outs[variant] = b.spmm_csr(rp, ci, va, M, K, Bd, variant=variant)
         check(outs[variant], ref, denom)
     # all CSR variants add the same terms in the same order with the same FMA: bit-identical
@@ -122,9 +116,10 @@ def test_csr_coo_ell_random(b, M, K, N, d, skew):
     check(got, refc, denom)
     assert (got == vals[0]).all().item()
     sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
-    got = b.spmm_sell(sp, sc, sv, M, K, Bd)
-    check(got, orc.spmm_ell(orc.csr_to_colell(a), B), denom)
-    assert (got == vals[0]).all().item()
+    for variant in (0, 1):
+        got = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=variant)
+        check(got, orc.spmm_ell(orc.csr_to_colell(a), B), denom)
+        assert (got == vals[0]).all().item()
 
 
 def test_noncontiguous_ldb_ldc(b):
@@ -155,6 +150,9 @@ def test_csr_staged_kernel(b, M, K, N, d):
     coo = orc.csr_to_coo(a)
     got2 = b.spmm_coo(b.dev_u32(coo.rowIdxs), ci, va, M, K, Bd, variant=2)
     assert (got2 == got).all().item()
+    sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
+    got3 = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=2)          # staged kernel on the sliced-ELL layout
+    assert (got3 == got).all().item()
 
 
 def test_staged_rejects_unsupported_shape(b):
@@ -342,5 +340,6 @@ def test_full_size_large_25605_properties(b):
     assert (cc == c3).all().item()
     del cc, rows
     sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
-    ce = b.spmm_sell(sp, sc, sv, M, K, Bd)
-    assert (ce == c3).all().item()
+    for variant in (1, 2):
+        ce = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=variant)
+        assert (ce == c3).all().item()
