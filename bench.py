@@ -207,16 +207,10 @@ def main():
     launches = int(L.cuspmm_launch_count())
     clocks = sampler.stop() if rank == 0 else None
     per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
-    total_ms = torch.tensor([sum(per_step)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    ms_per_step = total_ms / args.steps
-    nnz_all = torch.tensor([nnz], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(nnz_all, op=dist.ReduceOp.SUM)
-    flops_all = 2.0 * float(nnz_all.item()) * N
-    value = flops_all / (ms_per_step * 1e-3) / 1e9
+    sh = importlib.import_module("cuspmm_b200.sharding")
+    # whole-job throughput: all ranks' flops / the slowest rank's device time
+    value, ms_per_step = sh.job_throughput(sum(per_step), args.steps, flops, device="cuda")
+    flops_all = sh.reduce_sum(flops, device="cuda")
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     e2e = None

@@ -30,7 +30,6 @@
 namespace cuspmm_b200 {
 namespace bsrtc {
 
-constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr int kMaxTileN = 512;     // columns of C per CTA (4 UMMA M-tiles)
 
@@ -86,8 +85,12 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// ring depth: sized so that 3 CTAs fit on an SM for both block sizes (16.5 KB x 4 = 66 KB, 34 KB x 2 = 68 KB):
+// the prologue (TMEM alloc, barrier init) and the epilogue of one CTA then overlap the main loops of
+// the other two.  With 4 stages of 34 KB only one CTA fits and the 32x32 kernel was 2x slower.
 template <int BS>
 struct Smem {
+    static constexpr int kStages = BS == 16 ? 4 : 2;
     static constexpr uint32_t kBlockBytes = BS * BS * 2;
     static constexpr uint32_t kSlabBytes = BS * kMaxTileN * 2;          // bs k-rows x 512 n x 16 bit
     static constexpr uint32_t kStageBytes = kSlabBytes + kBlockBytes;
@@ -103,6 +106,7 @@ bsr_tc_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *__restr
               uint32_t Npad, uint32_t N, float *__restrict__ C, size_t ldc) {
     extern __shared__ __align__(128) unsigned char smem[];
     using S = Smem<BS>;
+    constexpr int kStages = S::kStages;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * S::kStageBytes);
     uint64_t *empty = full + kStages;
     uint64_t *accum_full = empty + kStages;
