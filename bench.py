@@ -247,6 +247,13 @@ def main():
         t_hbm = alg_bytes / (peak * 1e9) * 1e3
         t_fp32 = flops / (148 * 128 * 2 * sm_clock * 1e6) * 1e3
         t_l1 = (4.0 * nnz * N) / (148 * 128 * sm_clock * 1e6) * 1e3
+        traffic = None
+        try:     # measured once per kernel change with ncu --set full (never under the timed run)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if args.workload == "large_25605" and fmt == "csr" and args.variant in (0, 3):
+                traffic = tj["large_25605/csr/staged"]["bytes"]
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -260,7 +267,7 @@ def main():
             "gpu_launches": launches,
             "wall_ms_timed_region": wall_ms,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "kernel_ms": ms_per_step,
                          "bounds_ms": {"hbm": t_hbm, "fp32_fma": t_fp32, "smem_operand_bw": t_l1},

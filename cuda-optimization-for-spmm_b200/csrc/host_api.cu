@@ -95,10 +95,12 @@ extern "C" int cuspmm_spmm_csr_host(const uint32_t *rowPtrs, const uint32_t *col
     uint32_t *dRow = static_cast<uint32_t *>(hp.rowPtrs.p), *dCol = static_cast<uint32_t *>(hp.colIdxs.p);
     float *dVal = static_cast<float *>(hp.vals.p), *dB = static_cast<float *>(hp.B.p), *dC = static_cast<float *>(hp.C.p);
 
-    // panels: big enough that a panel kernel fills the GPU, small enough to overlap the copies
+    // panels: the staged kernel streams all of B once per 60-row CTA, so a panel must still give
+    // every SM a full CTA (>= ~6400 rows: 16 thin panels made the kernels 3x slower than the copies);
+    // within that, more panels = finer overlap of H2D(p+1) / kernel(p) / D2H(p-1)
     const size_t aBytes = (size_t)nnz * 8;
     uint32_t parts = (uint32_t)std::min<size_t>(kMaxPanels, std::max<size_t>(1, aBytes / (32u << 20)));
-    if (M < parts * 1024u) parts = std::max(1u, M / 1024u);
+    parts = std::min(parts, std::max(1u, (M + 3200u) / 6400u));
     const std::vector<uint32_t> sp = host_splits(rowPtrs, M, nnz, parts);
 
     CUSPMM_CUDA(cudaEventRecord(hp.t0, hp.up));

@@ -19,20 +19,50 @@
 
 namespace cuspmm_b200 {
 
+// =============================================================== row access (CSR or sliced ELL)
+// The row kernels below are written once against this accessor.  SELL = false: CSR, entry k of row r
+// at rowPtrs[r] + k.  SELL = true: sliced ELL (ptrs = slicePtrs), entry k of row r at
+// slicePtrs[r/32] + 32k + r%32, k < slice width; a row ends at its first padding entry (col kPad).
+template <bool SELL>
+struct RowRef {
+    uint32_t first, len;
+    static constexpr uint32_t stride = SELL ? 32u : 1u;
+    __device__ __forceinline__ RowRef(const uint32_t *__restrict__ ptrs, uint32_t r) {
+        if constexpr (SELL) {
+            const uint32_t sb = __ldg(ptrs + (r >> 5));
+            first = sb + (r & 31u);
+            len = (__ldg(ptrs + (r >> 5) + 1) - sb) >> 5;
+        } else {
+            first = __ldg(ptrs + r);
+            len = __ldg(ptrs + r + 1) - first;
+        }
+    }
+    __device__ __forceinline__ size_t at(uint32_t k) const { return (size_t)first + (size_t)k * stride; }
+};
+
 // =============================================================== variant 1 / 4
-// items = one per row + one per non-zero; warp w owns the rows whose first item falls
-// into [w*ipw, (w+1)*ipw).  Whole rows only, so no carries between warps.
+// items = one per row + one per non-zero (slot for ELL); warp w owns the rows whose first item
+// falls into [w*ipw, (w+1)*ipw).  Whole rows only, so no carries between warps.
+template <bool SELL>
 __device__ __forceinline__ void warp_row_range(const uint32_t *__restrict__ rowPtrs, uint32_t M,
                                                uint64_t ipw, uint32_t w, uint32_t &r0, uint32_t &r1) {
     // rowPtrs may be a row-panel VIEW of a larger matrix (rowPtrs[0] != 0, absolute offsets
     // into colIdxs/vals), so keys are taken relative to the panel's first entry.
     const uint32_t first = __ldg(rowPtrs);
-    auto key = [&](uint32_t p) -> uint64_t { return (uint64_t)(__ldg(rowPtrs + p) - first) + p; };
+    auto key = [&](uint32_t p) -> uint64_t {
+        if constexpr (SELL) {     // slots before row p: whole slices + p%32 rows of its own slice
+            const uint32_t sb = __ldg(rowPtrs + (p >> 5));
+            const uint32_t w32 = (p & 31u) ? ((__ldg(rowPtrs + (p >> 5) + 1) - sb) >> 5) * (p & 31u) : 0u;
+            return (uint64_t)(sb - first) + w32 + p;
+        } else {
+            return (uint64_t)(__ldg(rowPtrs + p) - first) + p;
+        }
+    };
     r0 = warp_lower_bound(M, (uint64_t)w * ipw, key);
     r1 = warp_lower_bound(M, (uint64_t)(w + 1) * ipw, key);
 }
 
-template <int U, int J>
+template <int U, int J, bool SELL>
 __global__ void __launch_bounds__(256)
 csr_rowsplit_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
                         const float *__restrict__ vals, uint32_t M, uint64_t ipw,
@@ -42,42 +72,43 @@ csr_rowsplit_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t col0 = blockIdx.y * (128u * U) + lane * 4u;   // first column of this lane
     uint32_t r0, r1;
-    warp_row_range(rowPtrs, M, ipw, w, r0, r1);
+    warp_row_range<SELL>(rowPtrs, M, ipw, w, r0, r1);
 
     bool valid[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) valid[u] = (col0 + u * 128u) < N;
 
     for (uint32_t r = r0; r < r1; ++r) {
-        const uint32_t start = __ldg(rowPtrs + r), end = __ldg(rowPtrs + r + 1);
+        const RowRef<SELL> row(rowPtrs, r);
         float4 acc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        for (uint32_t base = start; base < end; base += 32) {
-            const uint32_t idx = base + lane;
-            uint32_t mc = 0;
+        for (uint32_t base = 0; base < row.len; base += 32) {
+            const uint32_t k = base + lane;
+            uint32_t mc = kPad;
             float mv = 0.f;
-            if (idx < end) { mc = ld_stream(colIdxs + idx); mv = ld_stream(vals + idx); }
-            const int cnt = min(32u, end - base);
+            if (k < row.len) { mc = ld_stream(colIdxs + row.at(k)); mv = ld_stream(vals + row.at(k)); }
+            // valid entries form a prefix of the batch (ELL padding sits at the end of a row)
+            const int cnt = SELL ? __popc(__ballot_sync(0xFFFFFFFFu, mc != kPad)) : (int)min(32u, row.len - base);
             int j = 0;
             for (; j + J <= cnt; j += J) {
                 float4 b[J][U];
                 float v[J];
 #pragma unroll
-                for (int k = 0; k < J; ++k) {
-                    const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j + k);
-                    v[k] = __shfl_sync(0xFFFFFFFFu, mv, j + k);
+                for (int kk = 0; kk < J; ++kk) {
+                    const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j + kk);
+                    v[kk] = __shfl_sync(0xFFFFFFFFu, mv, j + kk);
                     const float *brow = B + (size_t)c * ldb + col0;
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (valid[u]) b[k][u] = __ldg(reinterpret_cast<const float4 *>(brow + u * 128));
+                        if (valid[u]) b[kk][u] = __ldg(reinterpret_cast<const float4 *>(brow + u * 128));
                 }
 #pragma unroll
-                for (int k = 0; k < J; ++k)
+                for (int kk = 0; kk < J; ++kk)
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (valid[u]) fma4(acc[u], v[k], b[k][u]);
+                        if (valid[u]) fma4(acc[u], v[kk], b[kk][u]);
             }
             for (; j < cnt; ++j) {
                 const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j);
@@ -87,6 +118,7 @@ csr_rowsplit_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__
                 for (int u = 0; u < U; ++u)
                     if (valid[u]) fma4(acc[u], v, __ldg(reinterpret_cast<const float4 *>(brow + u * 128)));
             }
+            if (SELL && cnt < 32) break;      // reached the padding: the row is finished
         }
         float *crow = C + (size_t)r * ldc + col0;
 #pragma unroll
@@ -95,7 +127,7 @@ csr_rowsplit_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__
     }
 }
 
-template <int U>
+template <int U, bool SELL>
 __global__ void __launch_bounds__(256)
 csr_rowsplit_scalar_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
                            const float *__restrict__ vals, uint32_t M, uint64_t ipw,
@@ -105,18 +137,18 @@ csr_rowsplit_scalar_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t 
     const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t col0 = blockIdx.y * (32u * U) + lane;
     uint32_t r0, r1;
-    warp_row_range(rowPtrs, M, ipw, w, r0, r1);
+    warp_row_range<SELL>(rowPtrs, M, ipw, w, r0, r1);
     for (uint32_t r = r0; r < r1; ++r) {
-        const uint32_t start = __ldg(rowPtrs + r), end = __ldg(rowPtrs + r + 1);
+        const RowRef<SELL> row(rowPtrs, r);
         float acc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) acc[u] = 0.f;
-        for (uint32_t base = start; base < end; base += 32) {
-            const uint32_t idx = base + lane;
-            uint32_t mc = 0;
+        for (uint32_t base = 0; base < row.len; base += 32) {
+            const uint32_t k = base + lane;
+            uint32_t mc = kPad;
             float mv = 0.f;
-            if (idx < end) { mc = ld_stream(colIdxs + idx); mv = ld_stream(vals + idx); }
-            const int cnt = min(32u, end - base);
+            if (k < row.len) { mc = ld_stream(colIdxs + row.at(k)); mv = ld_stream(vals + row.at(k)); }
+            const int cnt = SELL ? __popc(__ballot_sync(0xFFFFFFFFu, mc != kPad)) : (int)min(32u, row.len - base);
             for (int j = 0; j < cnt; ++j) {
                 const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j);
                 const float v = __shfl_sync(0xFFFFFFFFu, mv, j);
@@ -125,6 +157,7 @@ csr_rowsplit_scalar_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t 
                 for (int u = 0; u < U; ++u)
                     if (col0 + u * 32u < N) acc[u] = fmaf(v, __ldg(brow + col0 + u * 32u), acc[u]);
             }
+            if (SELL && cnt < 32) break;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -136,7 +169,7 @@ csr_rowsplit_scalar_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t 
 // G lanes per row (G*4 >= column tile), 32/G rows per warp; for narrow N a full warp
 // per row would leave most lanes idle.  Rows are dealt round-robin-free: row = global
 // group index (short-row regime, no balancing needed).
-template <int G>
+template <int G, bool SELL>
 __global__ void __launch_bounds__(256)
 csr_subwarp_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
                        const float *__restrict__ vals, uint32_t M,
@@ -148,20 +181,19 @@ csr_subwarp_vec_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__r
     const uint32_t col = blockIdx.y * (4u * G) + gl * 4u;
     const bool valid = col < N;
     const uint32_t r = gid;
-    uint32_t start = 0, end = 0;
-    if (r < M) { start = __ldg(rowPtrs + r); end = __ldg(rowPtrs + r + 1); }
-    const uint32_t len = end - start;
+    const RowRef<SELL> row(rowPtrs, r < M ? r : 0u);
+    const uint32_t len = r < M ? row.len : 0u;
     const uint32_t maxlen = __reduce_max_sync(0xFFFFFFFFu, len);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (uint32_t base = 0; base < maxlen; base += G) {
-        uint32_t mc = 0;
+        uint32_t mc = kPad;
         float mv = 0.f;
-        if (base + gl < len) { mc = ld_stream(colIdxs + start + base + gl); mv = ld_stream(vals + start + base + gl); }
+        if (base + gl < len) { mc = ld_stream(colIdxs + row.at(base + gl)); mv = ld_stream(vals + row.at(base + gl)); }
 #pragma unroll
         for (int j = 0; j < G; ++j) {
             const uint32_t c = __shfl_sync(0xFFFFFFFFu, mc, j, G);
             const float v = __shfl_sync(0xFFFFFFFFu, mv, j, G);
-            if (valid && base + j < len)
+            if (valid && c != kPad)                  // kPad: past the end of the row (or ELL padding)
                 fma4(acc, v, __ldg(reinterpret_cast<const float4 *>(B + (size_t)c * ldb + col)));
         }
     }
@@ -457,16 +489,13 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
     return 1;
 }
 
-// the staged kernel on a sliced-ELL matrix (spmm_ell.cu)
-int spmm_sell_staged(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
-                     const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
-    return staged::launch_by_N<true>(slicePtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-}
-
-int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
-                      uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
-                      float *C, size_t ldc, int variant, cudaStream_t st) {
-    CUSPMM_REQUIRE(variant >= 0 && variant <= CUSPMM_CSR_NUM_VARIANTS, "CSR variant %d does not exist", variant);
+// One dispatcher for both row layouts.  nnz = non-zeros (CSR) or slots (sliced ELL): only used
+// for load balancing and kernel selection.
+template <bool SELL>
+static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                         uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
+                         float *C, size_t ldc, int variant, cudaStream_t st) {
+    CUSPMM_REQUIRE(variant >= 0 && variant <= CUSPMM_CSR_NUM_VARIANTS, "%s variant %d does not exist", SELL ? "ELL row" : "CSR", variant);
     CUSPMM_REQUIRE(ldb >= N && ldc >= N, "ldb/ldc (%zu/%zu) must be >= N (%u)", ldb, ldc, N);
     if (M == 0 || N == 0) return CUSPMM_OK;
     CUSPMM_REQUIRE(rowPtrs && B && C && (nnz == 0 || (colIdxs && vals)), "null operand pointer");
@@ -486,13 +515,13 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
     case 1: {
         if (N > 256) {
             dim3 grid(blocks, (N + 511) / 512);
-            csr_rowsplit_vec_kernel<4, 2><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+            csr_rowsplit_vec_kernel<4, 2, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         } else if (N > 128) {
             dim3 grid(blocks, 1);
-            csr_rowsplit_vec_kernel<2, 4><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+            csr_rowsplit_vec_kernel<2, 4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         } else {
             dim3 grid(blocks, 1);
-            csr_rowsplit_vec_kernel<1, 8><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+            csr_rowsplit_vec_kernel<1, 8, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         }
         CUSPMM_LAUNCH_CHECK("csr_rowsplit_vec_kernel");
         return CUSPMM_OK;
@@ -501,25 +530,38 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
         const uint32_t G = N <= 16 ? 4 : (N <= 32 ? 8 : 16);
         const uint32_t rows_per_block = 256 / G;
         dim3 grid((M + rows_per_block - 1) / rows_per_block, (N + 4 * G - 1) / (4 * G));
-        if (G == 4) csr_subwarp_vec_kernel<4><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
-        else if (G == 8) csr_subwarp_vec_kernel<8><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
-        else csr_subwarp_vec_kernel<16><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
+        if (G == 4) csr_subwarp_vec_kernel<4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
+        else if (G == 8) csr_subwarp_vec_kernel<8, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
+        else csr_subwarp_vec_kernel<16, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
         CUSPMM_LAUNCH_CHECK("csr_subwarp_vec_kernel");
         return CUSPMM_OK;
     }
     case 3: {
         if (!(vok && N % 128 == 0))
-            return set_error(CUSPMM_ERR_UNSUPPORTED, "staged CSR kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
-        return staged::launch_by_N<false>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+            return set_error(CUSPMM_ERR_UNSUPPORTED, "staged kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
+        return staged::launch_by_N<SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);
-        csr_rowsplit_scalar_kernel<4><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        csr_rowsplit_scalar_kernel<4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         CUSPMM_LAUNCH_CHECK("csr_rowsplit_scalar_kernel");
         return CUSPMM_OK;
     }
     }
     return set_error(CUSPMM_ERR_INVALID, "unreachable");
+}
+
+int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                      uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
+                      float *C, size_t ldc, int variant, cudaStream_t st) {
+    return rows_dispatch<false>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, variant, st);
+}
+
+// the same kernels on a sliced-ELL matrix (called from spmm_ell.cu); variant numbering as CSR
+int spmm_sell_rows_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
+                            uint32_t M, uint32_t K, uint32_t slots, const float *B, uint32_t N, size_t ldb,
+                            float *C, size_t ldc, int variant, cudaStream_t st) {
+    return rows_dispatch<true>(slicePtrs, colIdxs, vals, M, K, slots, B, N, ldb, C, ldc, variant, st);
 }
 
 } // namespace cuspmm_b200

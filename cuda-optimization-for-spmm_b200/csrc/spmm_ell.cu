@@ -122,10 +122,11 @@ sell_scalar_kernel(const uint32_t *__restrict__ slicePtrs, const uint32_t *__res
     }
 }
 
-int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok);
-int spmm_sell_staged(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, const float *, uint32_t, size_t,
-                     float *, size_t, cudaStream_t);
+int spmm_sell_rows_dispatch(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, uint32_t,
+                            const float *, uint32_t, size_t, float *, size_t, int, cudaStream_t);
 
+// variants: 0 auto (the CSR selector applied to the slot count), 1 row kernels (warp / sub-warp per row,
+// nnz-balanced) reading the sliced layout, 2 staged TMA kernel, 3 slice per CTA (A staged through smem)
 static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
                               uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots, const float *B, uint32_t N,
                               size_t ldb, float *C, size_t ldc, int variant, cudaStream_t st) {
@@ -137,12 +138,12 @@ static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs
     const uint32_t slices = (M + kSliceH - 1) / kSliceH;
     const bool vok = (N % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    if (variant == 0) variant = (csr_select_variant(M, K, numSlots, N, vok) == 3) ? 2 : 1;   // slots ~ nnz
-    if (variant == 2) {
-        if (!(vok && N % 128 == 0))
-            return set_error(CUSPMM_ERR_UNSUPPORTED, "staged ELL kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
-        return spmm_sell_staged(slicePtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    if (variant == 0) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 0, st);
+    if (variant == 1) {   // row kernels; the selector chooses among warp / sub-warp / scalar, never staged
+        int v = (!vok) ? 4 : ((N < 128 || (double)numSlots / M < 96.0) ? 2 : 1);
+        return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, v, st);
     }
+    if (variant == 2) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 3, st);
     if (vok) {
         if (N > 256) sell_vec_kernel<4><<<dim3(slices, (N + 511) / 512), 256, 0, st>>>(slicePtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
         else if (N > 128) sell_vec_kernel<2><<<dim3(slices, 1), 256, 0, st>>>(slicePtrs, colIdxs, vals, M, B, N, ldb, C, ldc);

@@ -263,7 +263,7 @@ static DenseMatrix<DT, MT> *ellWrapper(int k, const char *name, SparseMatrixELL<
 }
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper1(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref) {
-    return ellWrapper<DT, MT, AccT>(1, "sell32_slice_per_cta", a, b, ref);
+    return ellWrapper<DT, MT, AccT>(1, "sell32_row_kernels", a, b, ref);
 }
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper2(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref) {

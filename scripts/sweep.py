@@ -47,7 +47,8 @@ def main():
     a = ap.parse_args()
     b = load_package().binding
     wl = importlib.import_module("cuspmm_b200.workloads")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")     # 256 MB, read (not written) to evict:
+    # a written flush buffer leaves ~126 MB of dirty lines whose write-back is charged to the next kernel
 
     def timeit(fn, cold):
         for _ in range(2):
@@ -55,7 +56,7 @@ def main():
         ts = []
         for _ in range(a.iters):
             if cold:
-                flush.zero_()
+                flush.sum()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); fn(); e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -76,8 +77,16 @@ def main():
         cold = byts["csr"] < 200e6
         tmp = torch.empty_like(Cd)
         try:
-            cus_avg, cus_min = b.cusparse_spmm(0, rp, ci, va, M, K, Bd, tmp, warmup=2, iters=a.iters)
-            coo_avg, _ = b.cusparse_spmm(1, rows, ci, va, M, K, Bd, tmp, warmup=2, iters=a.iters)
+            if cold:     # same protocol as ours: one timed launch after a read-flush of L2, median of iters
+                b.cusparse_spmm(0, rp, ci, va, M, K, Bd, tmp, warmup=2, iters=1)
+                c1, c2 = [], []
+                for _ in range(a.iters):
+                    flush.sum(); c1.append(b.cusparse_spmm(0, rp, ci, va, M, K, Bd, tmp, warmup=0, iters=1)[0])
+                    flush.sum(); c2.append(b.cusparse_spmm(1, rows, ci, va, M, K, Bd, tmp, warmup=0, iters=1)[0])
+                cus_avg, coo_avg = statistics.median(c1), statistics.median(c2)
+            else:
+                cus_avg, cus_min = b.cusparse_spmm(0, rp, ci, va, M, K, Bd, tmp, warmup=2, iters=a.iters)
+                coo_avg, _ = b.cusparse_spmm(1, rows, ci, va, M, K, Bd, tmp, warmup=2, iters=a.iters)
         except Exception as ex:
             cus_avg = coo_avg = float("nan")
             print(json.dumps({"config": name, "cusparse_error": str(ex)[:100]}), flush=True)
@@ -98,7 +107,7 @@ def main():
                    "t_hbm_ms": round(byts[fmt] / HBM / 1e6, 4), "t_fp32_ms": round(flops / 74.4e9, 4),
                    "t_smem_ms": round(4.0 * nnz * N / 37.2e9, 4),
                    "cusparse_ms": round(base, 4), "vs_cusparse": round(base / med, 2),
-                   "timing": "L2 flushed between iterations" if cold else "inputs larger than L2"}
+                   "timing": "L2 evicted by reading 256 MB between iterations (ours and cuSPARSE)" if cold else "inputs larger than L2"}
             print(json.dumps(rec), flush=True)
         del rp, ci, va, Bd, Cd, rows, sp, sc, sv, tmp
         torch.cuda.empty_cache()

@@ -116,7 +116,7 @@ def test_csr_coo_ell_random(b, M, K, N, d, skew):
     check(got, refc, denom)
     assert (got == vals[0]).all().item()
     sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
-    for variant in (0, 1):
+    for variant in (0, 1, 3):     # selector, row kernels on the sliced layout, slice-per-CTA kernel
         got = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=variant)
         check(got, orc.spmm_ell(orc.csr_to_colell(a), B), denom)
         assert (got == vals[0]).all().item()
@@ -179,7 +179,8 @@ def test_inf_in_unreferenced_B_rows_does_not_leak(b):
     for variant in (1, 2, 4):
         assert np.isfinite(b.spmm_csr(rp, ci, va, 100, 50, Bd, variant=variant).cpu().numpy()).all()
     sp, sc, sv = b.csr_to_sell(rp, ci, va, 100)
-    assert np.isfinite(b.spmm_sell(sp, sc, sv, 100, 50, Bd).cpu().numpy()).all()
+    for variant in (1, 3):
+        assert np.isfinite(b.spmm_sell(sp, sc, sv, 100, 50, Bd, variant=variant).cpu().numpy()).all()
 
 
 # ------------------------------------------------------------------ BSR fp32
@@ -340,6 +341,6 @@ def test_full_size_large_25605_properties(b):
     assert (cc == c3).all().item()
     del cc, rows
     sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         ce = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=variant)
         assert (ce == c3).all().item()
