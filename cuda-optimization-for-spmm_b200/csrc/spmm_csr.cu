@@ -455,7 +455,14 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
     static const int forceNT = getenv("CUSPMM_STAGED_NT") ? atoi(getenv("CUSPMM_STAGED_NT")) : 0;   // tuning hook
     if (forceNT == 128) return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (forceNT == 256 && N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    if (N % 512 == 0) return launch<Cfg<512, 15, 4, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    if (N % 512 == 0) {
+        // few rows per SM (M <= 30 * SMs, e.g. the 4096^2 configs): 2 rows per warp keeps all 15 consumer
+        // warps busy instead of half of them (latency hiding); otherwise 4 rows per warp (60-row panels)
+        const uint32_t sms = (uint32_t)sm_count();
+        if (M <= 30 * sms)
+            return launch<Cfg<512, 15, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        return launch<Cfg<512, 15, 4, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    }
     if (N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
 }
@@ -478,14 +485,14 @@ static uint32_t pick_warps(uint32_t M) {
 //   - no 128-bit loads possible                      -> scalar row-split (4)
 //   - N % 512 == 0, M >= 1024 and each staged B row is re-used by >= 2 rows of a 60-row panel
 //     (density * 60 >= 2)                            -> staged (3): B tiles through shared memory
-//   - narrow N (< 128) or short rows (< 96 nnz/row)  -> sub-warp per row (2)
+//   - narrow N (<= 128) or short rows (< 96 nnz/row)  -> sub-warp per row (2)
 //   - otherwise                                      -> warp per row, nnz-balanced (1)
 int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok) {
     if (!vec_ok) return 4;
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
     if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 2.0) return 3;
-    if (N < 128 || per_row < 96.0) return 2;
+    if (N <= 128 || per_row < 96.0) return 2;
     return 1;
 }
 
