@@ -47,10 +47,17 @@ struct HostPipe {
 };
 static HostPipe g_pipe[16];
 
-static std::vector<uint32_t> host_splits(const uint32_t *rowPtrs, uint32_t M, uint32_t nnz, uint32_t parts) {
+// Split points by nnz.  taper = false: equal shares (the multi-GPU rule).  taper = true: shares shrink
+// linearly towards the end (the host pipeline: the copies are the bottleneck, so what matters is how much
+// kernel + D2H is left once the last H2D lands -- a small last panel keeps that tail short).
+static std::vector<uint32_t> host_splits(const uint32_t *rowPtrs, uint32_t M, uint32_t nnz, uint32_t parts,
+                                         bool taper = false) {
     std::vector<uint32_t> s(parts + 1, 0);
+    const uint64_t wsum = (uint64_t)parts * (parts + 1) / 2;      // weights parts, parts-1, ..., 1
+    uint64_t wacc = 0;
     for (uint32_t g = 1; g < parts; ++g) {
-        const uint64_t t = ((uint64_t)g * nnz) / parts;
+        wacc += parts - (g - 1);
+        const uint64_t t = taper ? ((uint64_t)nnz * wacc) / wsum : ((uint64_t)g * nnz) / parts;
         s[g] = (uint32_t)(std::lower_bound(rowPtrs, rowPtrs + M + 1, (uint32_t)t) - rowPtrs);
         if (s[g] > M) s[g] = M;
         if (s[g] < s[g - 1]) s[g] = s[g - 1];
@@ -101,7 +108,8 @@ extern "C" int cuspmm_spmm_csr_host(const uint32_t *rowPtrs, const uint32_t *col
     const size_t aBytes = (size_t)nnz * 8;
     uint32_t parts = (uint32_t)std::min<size_t>(kMaxPanels, std::max<size_t>(1, aBytes / (32u << 20)));
     parts = std::min(parts, std::max(1u, (M + 3200u) / 6400u));
-    const std::vector<uint32_t> sp = host_splits(rowPtrs, M, nnz, parts);
+    if (parts >= 3) ++parts;     // tapering makes the early panels bigger, so one more of them is free
+    const std::vector<uint32_t> sp = host_splits(rowPtrs, M, nnz, parts, /*taper=*/true);
 
     CUSPMM_CUDA(cudaEventRecord(hp.t0, hp.up));
     CUSPMM_CUDA(cudaMemcpyAsync(dRow, rowPtrs, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice, hp.up));

@@ -183,6 +183,33 @@ def test_inf_in_unreferenced_B_rows_does_not_leak(b):
         assert np.isfinite(b.spmm_sell(sp, sc, sv, 100, 50, Bd, variant=variant).cpu().numpy()).all()
 
 
+def test_canaries_around_C_and_B(b):
+    """compute-sanitizer is closed on this pool: catch stray writes with sentinel rows around C and stray
+    reads with NaN rows around B (a NaN that leaks into C, or a changed sentinel, fails the test)."""
+    import torch
+    a = random_csr(1500, 600, 0.08, seed=77, skew=True)
+    N = 512
+    B = np.random.default_rng(78).uniform(-1, 1, (600, N)).astype(np.float32)
+    Bbig = torch.full((600 + 64, N), float("nan"), device="cuda")
+    Bbig[32:632] = b.dev_f32(B)
+    Bv = Bbig[32:632]
+    ref = orc.spmm_csr(a, B, omp=True)
+    denom = orc.absprod_csr(a, B)
+    rp, ci, va = dev_csr(b, a)
+    coo_rows = b.dev_u32(orc.csr_to_coo(a).rowIdxs)
+    sp, sc, sv = b.csr_to_sell(rp, ci, va, a.M)
+    runs = [(lambda out, v=v: b.spmm_csr(rp, ci, va, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2, 3, 4)]
+    runs += [(lambda out, v=v: b.spmm_coo(coo_rows, ci, va, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2)]
+    runs += [(lambda out, v=v: b.spmm_sell(sp, sc, sv, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2, 3)]
+    for run in runs:
+        Cbig = torch.full((a.M + 16, N), 12345.0, device="cuda")
+        out = Cbig[8:8 + a.M]
+        run(out)
+        torch.cuda.synchronize()
+        assert (Cbig[:8] == 12345.0).all().item() and (Cbig[8 + a.M:] == 12345.0).all().item()
+        check(out, ref, denom)
+
+
 # ------------------------------------------------------------------ BSR fp32
 @pytest.mark.parametrize("bs", [1, 2, 4, 16, 32])
 @pytest.mark.parametrize("N", [21, 128, 512])
