@@ -51,6 +51,8 @@ def lib():
         L.cuspmm_host_free.argtypes = [P]
         L.cuspmm_cusparse_spmm.argtypes = [C.c_int, P, P, P, U32, U32, U32, P, U32, P, C.c_int, C.c_int, C.c_int,
                                            C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.cuspmm_cusparse_spmm_bsr.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, P, C.c_int, C.c_int,
+                                               C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.cuspmm_mgpu_create_csr.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32]
         L.cuspmm_mgpu_set_B.argtypes = [P, P, U32]
         L.cuspmm_mgpu_run.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -258,6 +260,15 @@ def cusparse_spmm(fmt, rowOrPtr, colIdxs, vals, M, K, B, out, alg=0, warmup=3, i
     check(lib().cuspmm_cusparse_spmm(fmt, _ptr(rowOrPtr), _ptr(colIdxs), _ptr(vals), M, K, int(colIdxs.numel()), _ptr(B),
                                      B.shape[1], _ptr(out), alg, warmup, iters, C.byref(avg), C.byref(mn)),
           "cuspmm_cusparse_spmm")
+    return avg.value, mn.value
+
+
+def cusparse_spmm_bsr(blockRowPtrs, blockColIdxs, blocks, nbr, nbc, bs, B, out, warmup=2, iters=5):
+    avg, mn = C.c_float(0), C.c_float(0)
+    _torch().cuda.synchronize()
+    check(lib().cuspmm_cusparse_spmm_bsr(_ptr(blockRowPtrs), _ptr(blockColIdxs), _ptr(blocks), nbr, nbc,
+                                         int(blockColIdxs.numel()), bs, _ptr(B), B.shape[1], _ptr(out), warmup, iters,
+                                         C.byref(avg), C.byref(mn)), "cuspmm_cusparse_spmm_bsr")
     return avg.value, mn.value
 
 

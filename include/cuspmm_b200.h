@@ -211,6 +211,13 @@ int cuspmm_cusparse_spmm(int fmt, const uint32_t *rowOrPtr_dev, const uint32_t *
                          const float *B_dev, uint32_t N, float *C_dev,
                          int alg, int warmup, int iters, float *avg_ms, float *min_ms);
 
+/* cuSPARSE BSR SpMM (fp32 blocks, CUSPARSE_SPMM_ALG_DEFAULT): the descriptor the reference builds in
+ * src/formats/sparse_bsr.cu:139-155 but never runs (engine_bsr.hpp:24 SUPPORT_CUSPARSE = false). */
+int cuspmm_cusparse_spmm_bsr(const uint32_t *blockRowPtrs_dev, const uint32_t *blockColIdxs_dev, const float *blocks_dev,
+                             uint32_t numBlockRows, uint32_t numBlockCols, uint32_t numBlocks, uint32_t blockSize,
+                             const float *B_dev, uint32_t N, float *C_dev, int warmup, int iters,
+                             float *avg_ms, float *min_ms);
+
 #ifdef __cplusplus
 }
 #endif

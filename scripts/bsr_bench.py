@@ -62,6 +62,16 @@ def main():
         ref = Cd.clone()
         print(json.dumps({**base, "kernel": "bsr_f32_simt", "ms": round(med, 4), "tflops_executed": round(flops / med / 1e9, 2),
                           "alg_MB": round(byts / 1e6, 1), "hbm_frac": round(byts / med / 1e6 / HBM, 4)}), flush=True)
+        try:
+            tmp = torch.empty_like(Cd)
+            cavg, cmin = b.cusparse_spmm_bsr(rp, ci, blocks, nbr, nbc, bs, Bd, tmp, warmup=2, iters=a.iters)
+            cerr = ((tmp - ref).abs().max() / ref.abs().max()).item()
+            print(json.dumps({**base, "kernel": "cusparse_bsr_f32 (CUSPARSE_SPMM_ALG_DEFAULT)", "ms": round(cavg, 4), "ms_min": round(cmin, 4),
+                              "tflops_executed": round(flops / cavg / 1e9, 2), "max_abs_diff_vs_f32_kernel_over_max": cerr}), flush=True)
+            del tmp
+        except Exception as ex:
+            cavg = None
+            print(json.dumps({**base, "kernel": "cusparse_bsr_f32", "error": str(ex)[:160]}), flush=True)
         for dt in ("bf16", "fp16"):
             plan = b.BsrTcPlan(rp, ci, blocks, nbr, bs, Kp, N, dtype=dt)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -74,7 +84,8 @@ def main():
                               "tflops_executed": round(flops / med / 1e9, 2), "tensor_frac_of_measured_bf16": round(flops / med / 1e9 / TENSOR, 4),
                               "alg_MB": round(byts / 1e6, 1), "hbm_GBs": round(byts / med / 1e6, 1), "hbm_frac": round(byts / med / 1e6 / HBM, 4),
                               "l2_gather_GB": round(nb * bs * N * 2 / 1e9, 2), "prepare_B_ms": round(prep, 4),
-                              "max_abs_diff_vs_f32_kernel_over_max": err}), flush=True)
+                              "max_abs_diff_vs_f32_kernel_over_max": err,
+                              "vs_cusparse_bsr_f32": round(cavg / med, 2) if cavg else None}), flush=True)
             plan.close()
         del rp, ci, blocks, Bd, Cd, ref
         torch.cuda.empty_cache()
