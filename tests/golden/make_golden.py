@@ -61,8 +61,9 @@ def main():
                     shutil.copyfile(os.path.join(src, name), os.path.join(work, name))
             conv.process_mtx(work)
             for name in sorted(os.listdir(work)):
-                if not name.endswith(".mtx"):
-                    shutil.copyfile(os.path.join(work, name), os.path.join(out, name))
+                # converter outputs, plus the .mtx inputs themselves (a few KB) so that the native
+                # converter (host/cuspmm_convert) can be checked byte for byte without /root/reference
+                shutil.copyfile(os.path.join(work, name), os.path.join(out, name))
         files = os.listdir(out)
         pick = lambda suf: os.path.join(out, [f for f in files if f.endswith(suf)][0])  # noqa: E731
         B = orc.read_dense(pick("dense.in"))
