@@ -481,18 +481,19 @@ static uint32_t pick_warps(uint32_t M) {
     return (uint32_t)(want < M ? want : (M ? M : 1));
 }
 
-// Kernel selection (DESIGN.md "kernel selection"; measured in profiles/r01_sweep.jsonl):
-//   - no 128-bit loads possible                      -> scalar row-split (4)
-//   - N % 512 == 0, M >= 1024 and each staged B row is re-used by >= 2 rows of a 60-row panel
-//     (density * 60 >= 2)                            -> staged (3): B tiles through shared memory
-//   - narrow N (<= 128) or short rows (< 96 nnz/row)  -> sub-warp per row (2)
-//   - otherwise                                      -> warp per row, nnz-balanced (1)
+// Kernel selection (DESIGN.md "kernel selection"; measured in profiles/r01_sweep.jsonl and
+// profiles/r01_density_sweep_large_25605.txt):
+//   - no 128-bit loads possible                       -> scalar row-split (4)
+//   - N % 512 == 0, M >= 1024 and each staged B row is re-used often enough by a 60-row panel
+//     (density * 60 >= 1.6, i.e. >= ~2.7 % dense)     -> staged (3): B tiles through shared memory
+//   - N <= 512, or short rows (< 96 nnz/row)          -> sub-warp per row (2): 64-column tiles, many rows in flight
+//   - otherwise (wide N, long rows)                   -> warp per row, nnz-balanced (1): A is re-read N/512 times only
 int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok) {
     if (!vec_ok) return 4;
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
-    if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 2.0) return 3;
-    if (N <= 128 || per_row < 96.0) return 2;
+    if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 1.6) return 3;
+    if (N <= 512 || per_row < 96.0) return 2;
     return 1;
 }
 

@@ -140,7 +140,7 @@ static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs
                      ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     if (variant == 0) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 0, st);
     if (variant == 1) {   // row kernels; the selector chooses among warp / sub-warp / scalar, never staged
-        int v = (!vok) ? 4 : ((N <= 128 || (double)numSlots / M < 96.0) ? 2 : 1);
+        int v = (!vok) ? 4 : ((N <= 512 || (double)numSlots / M < 96.0) ? 2 : 1);
         return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, v, st);
     }
     if (variant == 2) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 3, st);
