@@ -49,7 +49,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        if (++spins > (1u << 24)) __trap();   // fail loudly instead of hanging the GPU
+        if (++spins > (1u << 27)) __trap();   // fail loudly instead of hanging the GPU
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {

@@ -237,7 +237,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (done) break;
-        if (++spins > (1u << 24)) __trap();   // a lost arrive must fail loudly, not hang the GPU
+        if (++spins > (1u << 27)) __trap();   // a lost arrive must fail loudly, not hang the GPU
     }
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
