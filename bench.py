@@ -47,18 +47,21 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+    nvidia-smi needs tens of ms before its first sample, so it is started before the warm-up and the
+    samples are filtered by their timestamps to [mark_start(), mark_end()]."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -67,28 +70,42 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for name, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
+
+        def collect(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                    for name, v in zip(names, r[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    pass
+            return sm, mx, pw, reasons
+        inside = [x for x in self.rows if self.t0 is not None and self.t0 - 0.02 <= x[0] <= (self.t1 or 1e18) + 0.03]
+        sm, mx, pw, reasons = collect(inside if inside else self.rows)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "window": "timed region" if inside else "whole run (no sample fell inside the timed region)",
+                "reasons": sorted(reasons)}
 
 
 def sample_rows_for_seconds(run_rows, target_s, start_rows=16, max_rows=None):
@@ -182,6 +199,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     if args.gather and world > 1:
@@ -189,12 +209,10 @@ def main():
         dist.all_gather(gathered, Cd)
     barrier()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     L.cuspmm_reset_launch_count()
     barrier()
+    sampler.mark_start()
     t_wall0 = time.perf_counter()
     for e0, e1 in evs:
         e0.record()
@@ -204,6 +222,7 @@ def main():
         e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    sampler.mark_end()
     launches = int(L.cuspmm_launch_count())
     clocks = sampler.stop() if rank == 0 else None
     per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
