@@ -420,6 +420,23 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
     }
 }
 
+// whole waves: (row panels x column tiles) is made a multiple of the SM count, rows per CTA =
+// ceil(M / panels) <= rowSlots
+struct GridPlan { uint32_t panels, rpc, waves; };
+static GridPlan plan_grid(uint32_t M, uint32_t ytiles, uint32_t rowSlots) {
+    const uint32_t sms = (uint32_t)sm_count();
+    const uint32_t minPanels = (M + rowSlots - 1) / rowSlots;
+    GridPlan g;
+    g.waves = (minPanels * ytiles + sms - 1) / sms;
+    g.panels = (g.waves * sms) / ytiles;
+    if (g.panels < minPanels) g.panels = minPanels;
+    g.rpc = (M + g.panels - 1) / g.panels;
+    if (g.rpc > rowSlots) g.rpc = rowSlots;
+    if (g.rpc == 0) g.rpc = 1;
+    g.panels = (M + g.rpc - 1) / g.rpc;
+    return g;
+}
+
 template <class CFG, bool SELL>
 int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
            const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
@@ -431,35 +448,34 @@ int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, 
         CUSPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::kSmemBytes));
         attr_done[dev & 63] = true;
     }
-    // whole waves: (row panels x column tiles) is made a multiple of the SM count, rows per CTA =
-    // ceil(M / panels) <= kRows
-    const uint32_t sms = (uint32_t)sm_count();
     const uint32_t ytiles = N / CFG::kNT;
-    const uint32_t minPanels = (M + CFG::kRows - 1) / CFG::kRows;
-    const uint32_t waves = (minPanels * ytiles + sms - 1) / sms;
-    uint32_t panels = (waves * sms) / ytiles;
-    if (panels < minPanels) panels = minPanels;
-    uint32_t rpc = (M + panels - 1) / panels;
-    if (rpc > (uint32_t)CFG::kRows) rpc = CFG::kRows;
-    if (rpc == 0) rpc = 1;
-    panels = (M + rpc - 1) / rpc;
-    dim3 grid(panels, ytiles);
-    kern<<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(rowPtrs, colIdxs, vals, M, K, rpc, B, N, ldb, C, ldc);
+    const GridPlan g = plan_grid(M, ytiles, CFG::kRows);
+    dim3 grid(g.panels, ytiles);
+    kern<<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(rowPtrs, colIdxs, vals, M, K, g.rpc, B, N, ldb, C, ldc);
     CUSPMM_LAUNCH_CHECK("csr_staged_kernel");
     return CUSPMM_OK;
 }
 
 template <bool SELL>
-int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
+int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                 const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
     static const int forceNT = getenv("CUSPMM_STAGED_NT") ? atoi(getenv("CUSPMM_STAGED_NT")) : 0;   // tuning hook
     if (forceNT == 128) return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (forceNT == 256 && N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (N % 512 == 0) {
-        // few rows per SM (M <= 30 * SMs, e.g. the 4096^2 configs): 2 rows per warp keeps all 15 consumer
-        // warps busy instead of half of them (latency hiding); otherwise 4 rows per warp (60-row panels)
-        const uint32_t sms = (uint32_t)sm_count();
-        if (M <= 30 * sms)
+        // 4 rows per warp (60-row panels) or 2 (30-row panels)?  Fewer rows per warp means more waves (B is
+        // streamed once per wave) but a shorter per-chunk critical path and all 15 warps busy on short panels.
+        // Cost model fitted on B200 (profiles/r01_staged_rw_tuning.txt): per wave  a_RW * K/20000  ms of
+        // chunk-loop latency (a_4 = 0.70, a_2 = 0.385) plus 4.4e-6 ms per non-zero of the panel's rows.
+        static const int forceRW = getenv("CUSPMM_STAGED_RW") ? atoi(getenv("CUSPMM_STAGED_RW")) : 0;   // tuning hook
+        const uint32_t ytiles = N / 512;
+        const double perRow = (double)nnz / (double)M;
+        auto cost = [&](uint32_t rowSlots, double a) {
+            const GridPlan g = plan_grid(M, ytiles, rowSlots);
+            return g.waves * (a * (double)K / 20000.0 + 4.4e-6 * perRow * g.rpc);
+        };
+        const bool two = forceRW ? forceRW == 2 : cost(30, 0.385) < cost(60, 0.70);
+        if (two)
             return launch<Cfg<512, 15, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         return launch<Cfg<512, 15, 4, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
@@ -547,7 +563,7 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
     case 3: {
         if (!(vok && N % 128 == 0))
             return set_error(CUSPMM_ERR_UNSUPPORTED, "staged kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
-        return staged::launch_by_N<SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        return staged::launch_by_N<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
     }
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);

@@ -23,10 +23,13 @@ def main():
     ap.add_argument("--N", type=int, default=0)
     ap.add_argument("--density", type=float, default=0.0)
     ap.add_argument("--cusparse", action="store_true")
+    ap.add_argument("--M", type=int, default=0)
     a = ap.parse_args()
     b = load_package().binding
     wl = importlib.import_module("cuspmm_b200.workloads")
     M, K, d, N = wl.NAMED[a.workload]
+    if a.M:
+        M = a.M
     if a.N:
         N = a.N
     if a.density:
