@@ -252,7 +252,7 @@ template <int NT, int NW, int RW, int KC, int STAGES>
 struct Cfg {
     static constexpr int kNT = NT, kNW = NW, kRW = RW, kKC = KC, kStages = STAGES;
     static constexpr int kRows = NW * RW;                     // row slots per CTA (upper bound)
-    static constexpr int kThreads = (NW + 1) * 32;            // 15 + 1 warps = 512 threads -> 128 regs/thread
+    static constexpr int kThreads = (NW + 1) * 32;            // 15+1 warps = 512 threads (128 regs) or 31+1 = 1024 (64 regs)
     static constexpr int kU = NT / 128;                       // float4 per lane per row
     static constexpr size_t kStageBytes = (size_t)KC * NT * sizeof(float);
     static constexpr size_t kSmemBytes = kStageBytes * STAGES + 2 * STAGES * sizeof(uint64_t) + 128;
@@ -463,20 +463,19 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
     if (forceNT == 128) return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (forceNT == 256 && N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (N % 512 == 0) {
-        // 4 rows per warp (60-row panels) or 2 (30-row panels)?  Fewer rows per warp means more waves (B is
-        // streamed once per wave) but a shorter per-chunk critical path and all 15 warps busy on short panels.
-        // Cost model fitted on B200 (profiles/r01_staged_rw_tuning.txt): per wave  a_RW * K/20000  ms of
-        // chunk-loop latency (a_4 = 0.70, a_2 = 0.385) plus 4.4e-6 ms per non-zero of the panel's rows.
+        // Three shapes of the same kernel (measured in profiles/r01_staged_rw_tuning.txt):
+        //   31 warps x 2 rows (1024 threads, 64 regs): 62-row panels, 8 warps per scheduler hide the
+        //       shuffle -> LDS -> FMA latency; shared-memory pipe bound.  Best whenever a CTA gets >= 30 rows.
+        //   15 warps x 2 rows: 30-row panels for short matrices (M < 30 * SMs): every warp still has work.
+        //   15 warps x 4 rows: the first version (60-row panels); kept behind the tuning hook only.
         static const int forceRW = getenv("CUSPMM_STAGED_RW") ? atoi(getenv("CUSPMM_STAGED_RW")) : 0;   // tuning hook
         const uint32_t ytiles = N / 512;
-        const double perRow = (double)nnz / (double)M;
-        auto cost = [&](uint32_t rowSlots, double a) {
-            const GridPlan g = plan_grid(M, ytiles, rowSlots);
-            return g.waves * (a * (double)K / 20000.0 + 4.4e-6 * perRow * g.rpc);
-        };
-        const bool two = forceRW ? forceRW == 2 : cost(30, 0.385) < cost(60, 0.70);
-        if (two)
-            return launch<Cfg<512, 15, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        int shape = forceRW;
+        // (sliced ELL keeps 15 x 4: its window refills are strided 128-byte-apart loads, and 16 warps sharing a
+        //  slice through a 30 KB L1 measured 6 % slower than 8 warps: 5.24 vs 4.92 ms on large_25605)
+        if (shape == 0) shape = plan_grid(M, ytiles, 62).rpc >= 30 ? (SELL ? 4 : 31) : 2;
+        if (shape == 31) return launch<Cfg<512, 31, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        if (shape == 2) return launch<Cfg<512, 15, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         return launch<Cfg<512, 15, 4, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
     if (N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
