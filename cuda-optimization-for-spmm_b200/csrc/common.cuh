@@ -88,6 +88,43 @@ __device__ __forceinline__ uint32_t warp_lower_bound(uint32_t n, uint64_t target
     }
     return lo;
 }
+
+// Two searches in lockstep (the lower and the upper end of a warp's row range): the two probe loads of a
+// round are issued back to back, so both searches together cost one dependent-load chain, not two.
+template <typename KeyFn>
+__device__ __forceinline__ void warp_lower_bound2(uint32_t n, uint64_t target0, uint64_t target1, KeyFn key,
+                                                  uint32_t &out0, uint32_t &out1) {
+    uint32_t lo0 = 0, hi0 = n, lo1 = 0, hi1 = n;
+    const uint32_t lane = lane_id();
+    while (lo0 < hi0 || lo1 < hi1) {
+        const uint32_t step0 = (hi0 - lo0) / 32u + 1u, step1 = (hi1 - lo1) / 32u + 1u;
+        const uint64_t q0 = (uint64_t)lo0 + (uint64_t)lane * step0, q1 = (uint64_t)lo1 + (uint64_t)lane * step1;
+        const uint32_t p0 = q0 > hi0 ? hi0 : (uint32_t)q0, p1 = q1 > hi1 ? hi1 : (uint32_t)q1;
+        const bool live0 = lo0 < hi0, live1 = lo1 < hi1;
+        const uint64_t k0 = (live0 && p0 < hi0) ? key(p0) : ~0ull;
+        const uint64_t k1 = (live1 && p1 < hi1) ? key(p1) : ~0ull;
+        if (live0) {
+            const int f = __ffs(__ballot_sync(0xFFFFFFFFu, k0 >= target0)) - 1;
+            if (f < 0) lo0 = lo0 + 31u * step0 + 1u;
+            else {
+                const uint32_t pf = __shfl_sync(0xFFFFFFFFu, p0, f), pp = __shfl_sync(0xFFFFFFFFu, p0, f > 0 ? f - 1 : 0);
+                hi0 = pf;
+                if (f > 0) lo0 = pp + 1;
+            }
+        }
+        if (live1) {
+            const int f = __ffs(__ballot_sync(0xFFFFFFFFu, k1 >= target1)) - 1;
+            if (f < 0) lo1 = lo1 + 31u * step1 + 1u;
+            else {
+                const uint32_t pf = __shfl_sync(0xFFFFFFFFu, p1, f), pp = __shfl_sync(0xFFFFFFFFu, p1, f > 0 ? f - 1 : 0);
+                hi1 = pf;
+                if (f > 0) lo1 = pp + 1;
+            }
+        }
+    }
+    out0 = lo0;
+    out1 = lo1;
+}
 #endif
 
 } // namespace cuspmm_b200

@@ -58,8 +58,7 @@ __device__ __forceinline__ void warp_row_range(const uint32_t *__restrict__ rowP
             return (uint64_t)(__ldg(rowPtrs + p) - first) + p;
         }
     };
-    r0 = warp_lower_bound(M, (uint64_t)w * ipw, key);
-    r1 = warp_lower_bound(M, (uint64_t)(w + 1) * ipw, key);
+    warp_lower_bound2(M, (uint64_t)w * ipw, (uint64_t)(w + 1) * ipw, key, r0, r1);
 }
 
 template <int U, int J, bool SELL>
