@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 namespace cuspmm_b200 {
@@ -46,6 +47,7 @@ struct HostPipe {
     bool init = false;
 };
 static HostPipe g_pipe[16];
+static std::mutex g_pipe_mutex[16];    // the per-device pipeline (streams, cached buffers) is used by one call at a time
 
 // Split points by nnz.  taper = false: equal shares (the multi-GPU rule).  taper = true: shares shrink
 // linearly towards the end (the host pipeline: the copies are the bottleneck, so what matters is how much
@@ -77,6 +79,7 @@ extern "C" int cuspmm_spmm_csr_host(const uint32_t *rowPtrs, const uint32_t *col
     if (M == 0 || N == 0) return CUSPMM_OK;
     int dev = 0;
     CUSPMM_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_pipe_mutex[dev & 15]);
     HostPipe &hp = g_pipe[dev & 15];
     constexpr int kMaxPanels = 16;
     if (!hp.init) {
@@ -167,6 +170,11 @@ extern "C" int cuspmm_mgpu_create_csr(cuspmmMgpuPlan *out, int ngpus, const int 
     CUSPMM_CUDA(cudaGetDeviceCount(&count));
     CUSPMM_REQUIRE(ngpus <= count, "asked for %d GPUs, %d visible", ngpus, count);
     auto *pl = new cuspmmMgpuPlan_s();
+    struct Guard {            // an error return below must not leak the half-built plan
+        cuspmmMgpuPlan_s *&p;
+        bool armed = true;
+        ~Guard() { if (armed && p) { cuspmm_mgpu_destroy(p); p = nullptr; } }
+    } guard{pl};
     pl->M = M; pl->K = K; pl->nnz = nnz; pl->maxN = maxN;
     pl->p.resize(ngpus);
     for (int g = 0; g < ngpus; ++g) pl->p[g].dev = devices ? devices[g] : g;
@@ -180,7 +188,7 @@ extern "C" int cuspmm_mgpu_create_csr(cuspmmMgpuPlan *out, int ngpus, const int 
         CUSPMM_CUDA(cudaMemcpy(dRow, rowPtrs, (size_t)(M + 1) * 4, cudaMemcpyHostToDevice));
         int rc = cuspmm_partition_rows_by_nnz(dRow, M, nnz, (uint32_t)ngpus, pl->splits.data(), nullptr);
         cudaFree(dRow);
-        if (rc) { delete pl; return rc; }
+        if (rc) return rc;
     }
     // peer access (all pairs that support it)
     pl->peer = true;
@@ -222,6 +230,7 @@ extern "C" int cuspmm_mgpu_create_csr(cuspmmMgpuPlan *out, int ngpus, const int 
     CUSPMM_CUDA(cudaMalloc(&pl->C0, (size_t)std::max(M, 1u) * maxN * 4));
     for (auto &q : pl->p) { CUSPMM_CUDA(cudaSetDevice(q.dev)); CUSPMM_CUDA(cudaStreamSynchronize(q.st)); }
     CUSPMM_CUDA(cudaSetDevice(pl->p[0].dev));
+    guard.armed = false;
     *out = pl;
     return CUSPMM_OK;
 }
@@ -303,12 +312,13 @@ extern "C" int cuspmm_mgpu_destroy(cuspmmMgpuPlan pl) {
     if (!pl) return CUSPMM_OK;
     for (auto &q : pl->p) {
         cudaSetDevice(q.dev);
+        if (q.st) cudaStreamSynchronize(q.st);
         cudaFree(q.rowPtrs); cudaFree(q.colIdxs); cudaFree(q.vals); cudaFree(q.B); cudaFree(q.C);
         if (q.st) cudaStreamDestroy(q.st);
         if (q.e0) cudaEventDestroy(q.e0);
         if (q.e1) cudaEventDestroy(q.e1);
     }
-    cudaSetDevice(pl->p[0].dev);
+    if (!pl->p.empty()) cudaSetDevice(pl->p[0].dev);
     cudaFree(pl->C0);
     delete pl;
     return CUSPMM_OK;

@@ -8,11 +8,14 @@
 //   variant 1  csr_rowsplit_vec   warp per row, lanes over columns (float4), rows dealt to
 //                                 warps in nnz-balanced contiguous ranges found by an
 //                                 in-kernel 32-ary search on rowPtrs (no preprocessing pass)
-//   variant 2  csr_subwarp_vec    "vector per row": G = 4/8/16 lanes per row for narrow N
+//   variant 2  csr_subwarp_vec    "vector per row": G = 4/8/16 lanes per row, 64-column tiles
 //   variant 3  csr_staged         row panel x K-chunks; each K-chunk of B is staged in shared
 //                                 memory by TMA bulk copies (cp.async.bulk + mbarrier ring,
-//                                 one producer warp) and re-used by all rows of the panel
+//                                 one producer warp) and re-used by all rows of the panel;
+//                                 31 consumer warps x 2 rows (or 15 x 2 / 15 x 4, see launch_by_N)
 //   variant 4  csr_rowsplit_scalar any N / ldb / alignment (N = 21 in data/small_210)
+// All row kernels are templated on the row accessor (RowRef<SELL>), so the same code runs on the
+// sliced-ELL layout (spmm_ell.cu calls spmm_sell_rows_dispatch).
 #include "common.cuh"
 
 #include <stdlib.h>

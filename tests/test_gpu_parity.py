@@ -371,3 +371,34 @@ def test_full_size_large_25605_properties(b):
     for variant in (1, 2, 3):
         ce = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=variant)
         assert (ce == c3).all().item()
+
+
+def test_full_size_ffn_shape_properties(b):
+    """BASELINE configs[4]: pruned-LLM FFN weight 11008x4096 at 50 % sparsity, N = 4096 tokens (22.5 M nnz,
+    C = 180 MB): the selector's kernel, the row-split kernel and COO agree bit for bit, and the checksum
+    1^T C == (1^T A) B holds in fp64."""
+    import importlib
+    import torch
+    wl = importlib.import_module("cuspmm_b200.workloads")
+    M, K, N = 11008, 4096, 4096
+    rp, ci, va = wl.gen_csr_device(M, K, 0.50, seed=7)
+    Bd = wl.gen_dense_device(K, N, seed=8)
+    c0 = b.spmm_csr(rp, ci, va, M, K, Bd, variant=0)
+    c1 = b.spmm_csr(rp, ci, va, M, K, Bd, variant=1)
+    assert (c0 == c1).all().item()
+    del c1
+    rows = torch.repeat_interleave(torch.arange(M, device="cuda", dtype=torch.int32), (rp[1:] - rp[:-1]).to(torch.int64))
+    cc = b.spmm_coo(rows, ci, va, M, K, Bd, variant=0)
+    assert (cc == c0).all().item()
+    del cc, rows
+    w = torch.zeros(K, dtype=torch.float64, device="cuda")
+    w.index_add_(0, ci.to(torch.int64), va.to(torch.float64))
+    expect = w @ Bd.to(torch.float64)
+    scale = w.abs() @ Bd.abs().to(torch.float64)
+    assert (((c0.to(torch.float64).sum(dim=0)) - expect).abs() / scale).max().item() < 1e-6
+    for r0 in (0, M - 16):
+        srp, sci, sva = wl.csr_sample_to_host(rp, ci, va, r0, r0 + 16)
+        a = orc.CSR(16, K, srp, sci, sva)
+        Bh = Bd.cpu().numpy()
+        err = orc.max_rel_err(c0[r0:r0 + 16].cpu().numpy(), orc.spmm_csr(a, Bh, omp=True), orc.absprod_csr(a, Bh))
+        assert err <= TOL, err
