@@ -57,3 +57,16 @@ def test_argument_validation_needs_no_device(L):
     assert rc == 1 and b"variant" in L.cuspmm_last_error()
     rc = L.cuspmm_spmm_csr(None, None, None, 4, 4, 0, None, 8, 4, None, 8, 1, None)
     assert rc == 1                                               # ldb < N
+
+
+def test_plain_c_client_compiles_links_and_runs(tmp_path):
+    """The header is C (not C++) and a gcc-built program links against the shared library."""
+    import subprocess
+    libdir = os.path.join(ROOT, "cuda-optimization-for-spmm_b200")
+    exe = str(tmp_path / "abi_c_client")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c_client.c"), "-o", exe, "-L", libdir, "-lcuspmm_b200",
+                    "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and "abi_c_client ok" in p.stdout, p.stdout + p.stderr
