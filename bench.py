@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="large_25605")
-    ap.add_argument("--format", default="csr", choices=["csr", "coo", "ell"])
+    ap.add_argument("--format", default="csr", choices=["csr", "coo", "ell", "bsr16", "bsr32"])
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--gather", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -175,14 +175,38 @@ def main():
     L = b.lib()
 
     M, K, density, N = wl.NAMED[args.workload]
-    rp, ci, va = wl.gen_csr_device(M, K, density, seed=618 + rank)
-    Bd = wl.gen_dense_device(K, N, seed=619)          # the same B on every rank (replicated operand)
-    nnz = int(ci.numel())
-    Cd = torch.empty((M, N), dtype=torch.float32, device="cuda")
-    flops = 2.0 * nnz * N
+    if not args.format.startswith("bsr"):
+        rp, ci, va = wl.gen_csr_device(M, K, density, seed=618 + rank)
+        Bd = wl.gen_dense_device(K, N, seed=619)          # the same B on every rank (replicated operand)
+        nnz = int(ci.numel())
+        Cd = torch.empty((M, N), dtype=torch.float32, device="cuda")
+        flops = 2.0 * nnz * N
 
     fmt = args.format
-    if fmt == "csr":
+    tensor = None
+    if fmt.startswith("bsr"):
+        # BASELINE configs[3]: the same M x K with 10 % of the bs x bs blocks stored, bf16 blocks on tcgen05
+        # tensor cores (fp32 accumulate in TMEM); "nnz" = stored block elements (executed flops)
+        bs = int(fmt[3:])
+        g = torch.Generator(device="cuda"); g.manual_seed(618 + rank)
+        nbr, nbc = (M + bs - 1) // bs, (K + bs - 1) // bs
+        mask = torch.rand((nbr, nbc), generator=g, device="cuda") < density
+        brp = torch.zeros(nbr + 1, dtype=torch.int64, device="cuda"); brp[1:] = torch.cumsum(mask.sum(dim=1, dtype=torch.int64), 0)
+        bci = mask.nonzero(as_tuple=False)[:, 1].to(torch.int32)
+        nb = int(bci.numel())
+        blocks = torch.rand(nb * bs * bs, generator=g, device="cuda") * 2 - 1
+        brp = brp.to(torch.int32)
+        Bd = wl.gen_dense_device(nbc * bs, N, seed=619)
+        M, K = nbr * bs, nbc * bs
+        Cd = torch.empty((M, N), dtype=torch.float32, device="cuda")
+        nnz = nb * bs * bs
+        flops = 2.0 * nnz * N
+        plan = b.BsrTcPlan(brp, bci, blocks, nbr, bs, K, N, dtype="bf16")
+        plan.prepare_B(Bd)
+        alg_bytes = 2 * nnz + 4 * nb + 4 * (nbr + 1) + 2 * K * N + 4 * M * N
+        step = lambda: plan.run(out=Cd)
+        tensor = True
+    elif fmt == "csr":
         alg_bytes = wl.csr_bytes(M, K, N, nnz)
         step = lambda: b.spmm_csr(rp, ci, va, M, K, Bd, variant=args.variant, out=Cd)
     elif fmt == "coo":
@@ -234,6 +258,8 @@ def main():
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     e2e = None
     try:
+        if tensor:
+            raise RuntimeError("the host-buffer entry point exists for CSR; BSR e2e not measured")
         rp_h, ci_h, va_h = rp.cpu().pin_memory(), ci.cpu().pin_memory(), va.cpu().pin_memory()
         B_h = Bd.cpu().pin_memory()
         C_h = torch.empty((M, N), dtype=torch.float32).pin_memory()
@@ -297,6 +323,26 @@ def main():
             "e2e": e2e,
             "clocks": clocks,
         }
+        if tensor:
+            tpeak = 1682.6
+            try:
+                tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            except Exception:
+                pass
+            tf = flops / (ms_per_step * 1e-3) / 1e12
+            out["dtype"] = "bf16 blocks and B, f32 accumulate"
+            out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                               "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)",
+                               "algorithmic_bytes_per_launch": alg_bytes, "hbm_GBs": achieved, "hbm_frac": achieved / peak,
+                               "binding": "l2_to_sm_operand_gather",
+                               "note": "at 10 % block density every stored block needs its own bs x N slab of B from L2 "
+                                       "(nb*bs*N*2 bytes): the kernel is bound by L2->SM bandwidth (ncu: lts 68 %), not the tensor pipe"}
+            try:
+                tmp = torch.empty_like(Cd)
+                avg, mn = b.cusparse_spmm_bsr(brp, bci, blocks, nbr, nbc, bs, Bd, tmp, warmup=1, iters=3)
+                out["cusparse"] = {"alg": "BSR fp32 ALG_DEFAULT", "ms_avg": avg, "speedup_vs_cusparse": avg / ms_per_step}
+            except Exception as ex:
+                out["cusparse"] = {"error": str(ex)[:200]}
         # ---- same-run cuSPARSE baseline
         if not args.no_cusparse and fmt in ("csr", "coo"):
             try:
@@ -312,7 +358,7 @@ def main():
             except Exception as ex:
                 out["cusparse"] = {"error": str(ex)[:200]}
         # ---- CPU baseline: bounded row sample of the same workload, this box's host cores
-        if world == 1:
+        if world == 1 and not tensor:
             try:
                 rows_cap = min(M, 4096)
                 srp, sci, sva = wl.csr_sample_to_host(rp, ci, va, 0, rows_cap)
