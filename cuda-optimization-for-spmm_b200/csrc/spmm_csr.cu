@@ -14,6 +14,8 @@
 //                                 one producer warp) and re-used by all rows of the panel;
 //                                 31 consumer warps x 2 rows (or 15 x 2 / 15 x 4, see launch_by_N)
 //   variant 4  csr_rowsplit_scalar any N / ldb / alignment (N = 21 in data/small_210)
+//   variant 5  csr_tmem           variant 3's design with the B chunks in tensor memory, read with
+//                                 tcgen05.ld instead of LDS (spmm_csr_tmem.cu)
 // All row kernels are templated on the row accessor (RowRef<SELL>), so the same code runs on the
 // sliced-ELL layout (spmm_ell.cu calls spmm_sell_rows_dispatch).
 #include "common.cuh"
@@ -486,6 +488,11 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
 
 } // namespace staged
 
+// variant 5: the staged design with the B chunks in tensor memory (spmm_csr_tmem.cu)
+template <bool SELL>
+int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
+                   const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
+
 // =============================================================== host dispatch
 static bool vec_ok(const float *B, size_t ldb, const float *C, size_t ldc, uint32_t N) {
     return (N % 4 == 0) && (ldb % 4 == 0) && (ldc % 4 == 0) &&
@@ -565,6 +572,11 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
         if (!(vok && N % 128 == 0))
             return set_error(CUSPMM_ERR_UNSUPPORTED, "staged kernel needs N %% 128 == 0 and aligned B/C (N=%u)", N);
         return staged::launch_by_N<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
+    }
+    case 5: {
+        if (!(vok && N % 512 == 0))
+            return set_error(CUSPMM_ERR_UNSUPPORTED, "TMEM-staged kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
+        return spmm_rows_tmem<SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);

@@ -155,12 +155,35 @@ def test_csr_staged_kernel(b, M, K, N, d):
     assert (got3 == got).all().item()
 
 
+@pytest.mark.parametrize("M,K,N,d,skew", [(3000, 1024, 512, 0.05, False), (1111, 777, 1024, 0.08, False),
+                                          (2048, 1000, 512, 0.30, False), (1500, 2051, 512, 0.06, True),
+                                          (61, 15, 512, 0.5, False), (5000, 333, 2048, 0.02, True)])
+def test_csr_tmem_kernel(b, M, K, N, d, skew):
+    """Variant 5: B chunks staged in tensor memory (tcgen05.cp), gathered with tcgen05.ld.  Same fp32 FMAs in the
+    same order as the other variants: checked against the oracle AND bit-identical to variant 1; covers K not a
+    multiple of the 16-row chunk, column tiles with ldb != 512, long rows (window refills), skewed rows."""
+    a = random_csr(M, K, d, seed=N + M, skew=skew)
+    B = np.random.default_rng(1).uniform(-1, 1, (K, N)).astype(np.float32)
+    Bd = b.dev_f32(B)
+    rp, ci, va = dev_csr(b, a)
+    got = b.spmm_csr(rp, ci, va, M, K, Bd, variant=5)
+    check(got, orc.spmm_csr(a, B, omp=True), orc.absprod_csr(a, B))
+    assert (got == b.spmm_csr(rp, ci, va, M, K, Bd, variant=1)).all().item()
+    sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
+    got3 = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=4)          # the same kernel on the sliced-ELL layout
+    assert (got3 == got).all().item()
+    # run to run: no atomics, fixed order
+    assert (b.spmm_csr(rp, ci, va, M, K, Bd, variant=5) == got).all().item()
+
+
 def test_staged_rejects_unsupported_shape(b):
     a = random_csr(64, 64, 0.1, seed=1)
     rp, ci, va = dev_csr(b, a)
     Bd = b.dev_f32(np.ones((64, 100), np.float32))
     with pytest.raises(b.CuspmmError):
         b.spmm_csr(rp, ci, va, 64, 64, Bd, variant=3)
+    with pytest.raises(b.CuspmmError):
+        b.spmm_csr(rp, ci, va, 64, 64, Bd, variant=5)     # N % 512 != 0
     with pytest.raises(b.CuspmmError):
         b.spmm_csr(rp, ci, va, 64, 64, Bd, variant=9)     # "Not implemented" (engine_csr.hpp:88)
 
@@ -198,9 +221,9 @@ def test_canaries_around_C_and_B(b):
     rp, ci, va = dev_csr(b, a)
     coo_rows = b.dev_u32(orc.csr_to_coo(a).rowIdxs)
     sp, sc, sv = b.csr_to_sell(rp, ci, va, a.M)
-    runs = [(lambda out, v=v: b.spmm_csr(rp, ci, va, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2, 3, 4)]
+    runs = [(lambda out, v=v: b.spmm_csr(rp, ci, va, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2, 3, 4, 5)]
     runs += [(lambda out, v=v: b.spmm_coo(coo_rows, ci, va, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2)]
-    runs += [(lambda out, v=v: b.spmm_sell(sp, sc, sv, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2, 3)]
+    runs += [(lambda out, v=v: b.spmm_sell(sp, sc, sv, a.M, a.K, Bv, variant=v, out=out)) for v in (1, 2, 3, 4)]
     for run in runs:
         Cbig = torch.full((a.M + 16, N), 12345.0, device="cuda")
         out = Cbig[8:8 + a.M]
@@ -345,6 +368,9 @@ def test_full_size_large_25605_properties(b):
     c3 = b.spmm_csr(rp, ci, va, M, K, Bd, variant=3)
     c1 = b.spmm_csr(rp, ci, va, M, K, Bd, variant=1)
     assert (c1 == c3).all().item()
+    c5 = b.spmm_csr(rp, ci, va, M, K, Bd, variant=5)          # B through tensor memory
+    assert (c5 == c3).all().item()
+    del c1, c5
     # (1) sampled rows vs oracle
     for r0 in (0, 12800, M - 37):
         r1 = min(M, r0 + 37)
@@ -368,7 +394,7 @@ def test_full_size_large_25605_properties(b):
     assert (cc == c3).all().item()
     del cc, rows
     sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
-    for variant in (1, 2, 3):
+    for variant in (1, 2, 3, 4):
         ce = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=variant)
         assert (ce == c3).all().item()
 
