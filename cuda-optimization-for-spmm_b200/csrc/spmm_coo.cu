@@ -158,7 +158,8 @@ static int spmm_coo_dispatch(const uint32_t *rowIdxs, const uint32_t *colIdxs, c
                      ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     if (variant == 0) {   // the CSR selector decides whether the staged kernel pays; it needs row pointers
         const bool have_ws = ws && ws_bytes >= (size_t)(M + 1) * 4;
-        variant = (have_ws && csr_select_variant(M, K, nnz, N, vok) == 3) ? 2 : 1;
+        const int cv = csr_select_variant(M, K, nnz, N, vok);
+        variant = (have_ws && (cv == 3 || cv == 5)) ? 2 : 1;
     }
     if (variant == 2) {
         if (ws_bytes < (size_t)(M + 1) * 4 || !ws)

@@ -490,8 +490,9 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
 
 // variant 5: the staged design with the B chunks in tensor memory (spmm_csr_tmem.cu)
 template <bool SELL>
-int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
+int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                    const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
+int tmem_rows_per_cta();
 
 // =============================================================== host dispatch
 static bool vec_ok(const float *B, size_t ldb, const float *C, size_t ldc, uint32_t N) {
@@ -510,13 +511,19 @@ static uint32_t pick_warps(uint32_t M) {
 //   - no 128-bit loads possible                       -> scalar row-split (4)
 //   - N % 512 == 0, M >= 1024 and each staged B row is re-used often enough by a 60-row panel
 //     (density * 60 >= 1.6, i.e. >= ~2.7 % dense)     -> staged (3): B tiles through shared memory
+//     ... and density >= 12 % with a full wave of CTAs -> dual-path staged (5): part of every B chunk in tensor memory
 //   - N <= 512, or short rows (< 96 nnz/row)          -> sub-warp per row (2): 64-column tiles, many rows in flight
 //   - otherwise (wide N, long rows)                   -> warp per row, nnz-balanced (1): A is re-read N/512 times only
 int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok) {
     if (!vec_ok) return 4;
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
-    if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 1.6) return 3;
+    if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 1.6) {
+        // staged; from ~12 % density on, with at least one full wave of CTAs, the dual-path kernel (5) is faster:
+        // its TMEM round trip needs long enough chunks to hide behind (measured in spmm_csr_tmem.cu)
+        const uint64_t ctas = (uint64_t)((M + tmem_rows_per_cta() - 1) / tmem_rows_per_cta()) * (N / 512);
+        return (density >= 0.12 && ctas >= (uint64_t)sm_count()) ? 5 : 3;
+    }
     if (N <= 512 || per_row < 96.0) return 2;
     return 1;
 }
@@ -576,7 +583,7 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
     case 5: {
         if (!(vok && N % 512 == 0))
             return set_error(CUSPMM_ERR_UNSUPPORTED, "TMEM-staged kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
-        return spmm_rows_tmem<SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        return spmm_rows_tmem<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
     }
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);

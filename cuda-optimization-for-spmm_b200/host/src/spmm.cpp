@@ -200,6 +200,7 @@ CSR_WRAPPER(1, "csr_rowsplit_vec")
 CSR_WRAPPER(2, "csr_subwarp_vec")
 CSR_WRAPPER(3, "csr_staged_tma")
 CSR_WRAPPER(4, "csr_rowsplit_scalar")
+CSR_WRAPPER(5, "csr_staged_tma_tmem")
 
 // ------------------------------------------------------------------------------- COO wrappers
 template <typename DT, typename MT, typename AccT>
@@ -334,6 +335,7 @@ template Dn *spmmCSRWrapper1<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper2<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper3<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper4<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
+template Dn *spmmCSRWrapper5<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper1<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper2<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmELLWrapper1<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);

@@ -60,8 +60,9 @@ int cuspmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
  *   2  vector-per-row: sub-warp per row for narrow N / short rows
  *   3  staged: row panel x K-chunks, B tiles staged in shared memory by TMA bulk copies
  *   4  scalar generic (any N, any alignment)
- *   5  staged through tensor memory: as 3, but the B chunks are copied on into TMEM
- *      (tcgen05.cp) and gathered with tcgen05.ld; fp32 FMA in CSR order like 1..4
+ *   5  staged, dual operand path: as 3, and the first rows of every B chunk are copied on
+ *      into tensor memory (tcgen05.cp) and gathered from there with tcgen05.ld, which
+ *      takes those non-zeros off the shared-memory pipe; fp32 FMA in CSR order like 1..4
  *      (N % 512 == 0, else CUSPMM_ERR_UNSUPPORTED) */
 #define CUSPMM_CSR_NUM_VARIANTS 5
 int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
@@ -91,7 +92,7 @@ int cuspmm_spmm_coo(const uint32_t *rowIdxs_dev, const uint32_t *colIdxs_dev, co
  * (include/engine/engine_ell.hpp:15-19, src/spmm/ell/spmm_ell_k{1,2}.cu). */
 #define CUSPMM_ELL_NUM_VARIANTS 4 /* 1 row kernels (warp / sub-warp per row); 2 staged (B tiles via TMA bulk
                                      copies); 3 slice per CTA with the slots staged through shared memory;
-                                     4 staged through tensor memory (CSR variant 5 on the sliced layout) */
+                                     4 staged with the dual operand path (CSR variant 5 on the sliced layout) */
 int cuspmm_spmm_sell(const uint32_t *slicePtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
                      uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots /* = slicePtrs[numSlices] */,
                      const float *B_dev, uint32_t N, size_t ldb,

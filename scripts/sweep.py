@@ -31,6 +31,8 @@ CONFIGS = [
     ("cfg3 medium_4000 s50 N512", 4000, 4000, 0.50, 512),
     ("cfg3 medium_4000 s50 N2048", 4000, 4000, 0.50, 2048),
     ("cfg4 large_25605 s90 N512", 25605, 25605, 0.10, 512),
+    ("cfg4 large_25605 s70 N512", 25605, 25605, 0.30, 512),
+    ("cfg4 large_25605 s50 N512", 25605, 25605, 0.50, 512),
     ("cfg5 ffn_11008x4096 s90 N4096", 11008, 4096, 0.10, 4096),
     ("cfg5 ffn_11008x4096 s70 N4096", 11008, 4096, 0.30, 4096),
     ("cfg5 ffn_11008x4096 s50 N4096", 11008, 4096, 0.50, 4096),
@@ -90,9 +92,9 @@ def main():
         except Exception as ex:
             cus_avg = coo_avg = float("nan")
             print(json.dumps({"config": name, "cusparse_error": str(ex)[:100]}), flush=True)
-        kernels = [("csr", v, (lambda v=v: b.spmm_csr(rp, ci, va, M, K, Bd, variant=v, out=Cd))) for v in (0, 1, 2, 3)]
+        kernels = [("csr", v, (lambda v=v: b.spmm_csr(rp, ci, va, M, K, Bd, variant=v, out=Cd))) for v in (0, 1, 2, 3, 5)]
         kernels += [("coo", v, (lambda v=v: b.spmm_coo(rows, ci, va, M, K, Bd, variant=v, out=Cd))) for v in (1, 2)]
-        kernels += [("ell", v, (lambda v=v: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=v, out=Cd))) for v in (0, 1, 2)]
+        kernels += [("ell", v, (lambda v=v: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=v, out=Cd))) for v in (0, 1, 2, 4)]
         for fmt, v, fn in kernels:
             try:
                 med, mn = timeit(fn, cold)

@@ -72,9 +72,9 @@ def test_cli_all_formats_on_reference_fixtures(case):
     for r in recs:
         by_fmt.setdefault(r["format"], []).append(r)
     assert set(by_fmt) == {"CSR", "COO", "BSR", "ELL"}
-    # CSR: kernel 0 (CPU), 1..4, cuSPARSE (-1)
+    # CSR: kernel 0 (CPU), 1..4 as the reference numbers them + 5 (dual-path staged, additive), cuSPARSE (-1)
     kinds = [r["kernelType"] for r in by_fmt["CSR"]]
-    assert kinds == ["0", "1", "2", "3", "4", "-1"]
+    assert kinds == ["0", "1", "2", "3", "4", "5", "-1"]
     n_cols = int(open(os.path.join(d, "dense.in")).readline().split()[1])
     for r in recs:
         k, fmt = r["kernelType"], r["format"]
@@ -82,6 +82,8 @@ def test_cli_all_formats_on_reference_fixtures(case):
             assert r["correct"] == "0"          # 1x1 blocks: the tensor-core variants decline (cf. spmm_csr_k4.cu:97-101)
         elif (fmt == "CSR" and k == "3" or fmt == "ELL" and k == "2") and n_cols % 128:
             assert r["correct"] == "0"          # the staged variant declines N it cannot tile (cf. spmm_csr_k4.cu:97-101)
+        elif fmt == "CSR" and k == "5" and n_cols % 512:
+            assert r["correct"] == "0"          # the dual-path kernel tiles N by 512
         else:
             assert r["correct"] == "1", r
         assert r["denseOrdering"] == "ROW_MAJOR"
@@ -136,7 +138,7 @@ def test_cli_on_generated_directory(tmp_path):
     subprocess.run(["python", os.path.join(ROOT, "scripts", "gen_data.py"), d, "--rows", "1024", "--cols", "768", "--density", "0.1",
                     "--N", "512", "--range", "-1", "1", "--bsr-block", "16"], check=True, capture_output=True)
     recs = records(run("--csr", "--coo", "--ell", "--bsr", "-d", d, "--iters", "2").stdout)
-    assert len(recs) == 6 + 4 + 3 + 4
+    assert len(recs) == 7 + 4 + 3 + 4
     for r in recs:
         if r["format"] == "BSR" and r["kernelType"] in ("2", "3"):
             # bf16/fp16 operand rounding (2^-9 / 2^-12 per operand) is judged with its own tolerance in
