@@ -519,10 +519,11 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
     if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 1.6) {
-        // staged; from ~12 % density on, with at least one full wave of CTAs, the dual-path kernel (5) is faster:
-        // its TMEM round trip needs long enough chunks to hide behind (measured in spmm_csr_tmem.cu)
+        // staged; from ~12 % density on (15 % when the column tile is narrower than B, i.e. row-wise TMA copies), with at
+        // least one full wave of CTAs, the dual-path kernel (5) is faster: its TMEM round trip needs long enough chunks to
+        // hide behind (d = 0.10: -6 % .. +20 % depending on the shape; d = 0.12 .. 0.5: 4 .. 32 % faster; spmm_csr_tmem.cu)
         const uint64_t ctas = (uint64_t)((M + tmem_rows_per_cta() - 1) / tmem_rows_per_cta()) * (N / 512);
-        return (density >= 0.12 && ctas >= (uint64_t)sm_count()) ? 5 : 3;
+        return (density >= (N == 512 ? 0.12 : 0.15) && ctas >= (uint64_t)sm_count()) ? 5 : 3;
     }
     if (N <= 512 || per_row < 96.0) return 2;
     return 1;

@@ -463,7 +463,7 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
         // ------------------------------------------------------------ consumers
         uint32_t wbase[RW], wj[RW], end[RW], bcol[RW], off[RW];
         float bval[RW];
-        unsigned long long acc[RW][8];         // acc[i][2u + h] = columns 128u + 4 lane + 2h, +1 (packed fp32x2)
+        float2 acc[RW][8];                     // acc[i][2u + h] = columns 128u + 4 lane + 2h, +1 (packed fp32x2 FMAs)
         auto refill = [&](int i, uint32_t from) {
             wbase[i] = from;
             wj[i] = 0;
@@ -496,19 +496,22 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
             off[i] = __shfl_sync(0xFFFFFFFFu, off[i], 0);
             refill(i, p0);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[i][e] = 0ull;
+            for (int e = 0; e < 8; ++e) acc[i][e] = make_float2(0.f, 0.f);
         }
         const uint32_t tq = tmem_base + (((warp & 3u) * 32u) << 16);     // this warp's lane quarter
 
+        // __ffma2_rn: packed fp32x2 FMA (FFMA2), per component the same IEEE fma as fmaf(), half the issue slots
         auto fma_row = [&](int i, float v, const uint32_t (&b)[16]) {
-            unsigned long long v2;
-            asm("mov.b64 %0, {%1, %1};" : "=l"(v2) : "r"(__float_as_uint(v)));
+            const float2 v2 = make_float2(v, v);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ffma2(acc[i][e], v2, b[2 * e], b[2 * e + 1]);
+            for (int e = 0; e < 8; ++e)
+                acc[i][e] = __ffma2_rn(v2, make_float2(__uint_as_float(b[2 * e]), __uint_as_float(b[2 * e + 1])), acc[i][e]);
         };
-        auto from_tmem = [&](int i, uint32_t cbase, uint32_t c, float v) {
+        // cbase_v: TMEM address of column k0's row (stage base - 16 k0), kept in ONE vector register per chunk; the address
+        // of a B row is formed with one LEA and moved to the uniform file (ptxas otherwise re-derives the base for every entry)
+        auto from_tmem = [&](int i, uint32_t cbase_v, uint32_t c, float v) {
             uint32_t b[16];
-            tmem_ld16_wait(cbase + (c << 4), b);
+            tmem_ld16_wait(cbase_v + (c << 4), b);
             fma_row(i, v, b);
         };
         // shared-space address of this lane's 16 bytes of row 0 / stage 0, made opaque so that it stays in ONE register
@@ -541,7 +544,8 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
             mbar_wait(full + s, (ch / STAGES) & 1);
             tc_fence_after();
             const uint32_t tile = lane_sa + s * kStageBytes - k0 * kRowBytes;       // stage row 0 = column k0 (mod 2^32)
-            const uint32_t cbase = tq + ts * (TR * 16) - (k0 << 4);
+            uint32_t cbase = tq + ts * (TR * 16) - (k0 << 4);
+            asm volatile("" : "+r"(cbase));
             // t-th entry of both rows together while both have one (their shuffles are issued back to back, so the
             // second row's broadcast latency hides behind the first row's loads), then the longer row's tail
             static_assert(RW == 2, "the fused loop below is written for two rows per warp");
@@ -600,10 +604,10 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     float4 o;
-                    o.x = __uint_as_float((uint32_t)acc[i][2 * u]);
-                    o.y = __uint_as_float((uint32_t)(acc[i][2 * u] >> 32));
-                    o.z = __uint_as_float((uint32_t)acc[i][2 * u + 1]);
-                    o.w = __uint_as_float((uint32_t)(acc[i][2 * u + 1] >> 32));
+                    o.x = acc[i][2 * u].x;
+                    o.y = acc[i][2 * u].y;
+                    o.z = acc[i][2 * u + 1].x;
+                    o.w = acc[i][2 * u + 1].y;
                     __stcs(crow + u * 32, o);
                 }
             }
