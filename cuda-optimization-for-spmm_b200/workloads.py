@@ -18,6 +18,8 @@ NAMED = {
     "medium_4000_s90": (4000, 4000, 0.10, 512),
     "medium_4000_s50": (4000, 4000, 0.50, 512),
     "large_25605": (25605, 25605, 0.10, 512),        # north-star target row (configs[3] CSR/COO/ELL)
+    "large_25605_s70": (25605, 25605, 0.30, 512),    # the same shape across the sparsity sweep of configs[2]
+    "large_25605_s50": (25605, 25605, 0.50, 512),
     "large_20000": (20000, 20000, 0.10, 512),        # configs[4] row-sharded
     "ffn_11008x4096_s90": (11008, 4096, 0.10, 4096),
     "ffn_11008x4096_s50": (11008, 4096, 0.50, 4096),
