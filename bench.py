@@ -295,8 +295,12 @@ def main():
         traffic = None
         try:     # measured once per kernel change with ncu --set full (never under the timed run)
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if args.workload == "large_25605" and fmt == "csr" and args.variant in (0, 3):
-                traffic = tj["large_25605/csr/staged"]["bytes"]
+            if fmt == "csr":      # variant 0 = the selector: dual-path kernel (5) on both workloads below
+                key = {("large_25605", 0): "large_25605/csr/dual", ("large_25605", 5): "large_25605/csr/dual",
+                       ("large_25605", 3): "large_25605/csr/staged", ("large_25605_s50", 0): "large_25605_s50/csr/dual",
+                       ("large_25605_s50", 5): "large_25605_s50/csr/dual"}.get((args.workload, args.variant))
+                if key:
+                    traffic = tj[key]["bytes"]
         except Exception:
             pass
         out = {
@@ -319,7 +323,8 @@ def main():
                          "binding": max((("hbm", t_hbm), ("fp32_fma", t_fp32), ("smem_operand_bw", t_l1)), key=lambda x: x[1])[0],
                          "frac_of_binding_bound": max(t_hbm, t_fp32, t_l1) / ms_per_step,
                          "note": "fp32 CUDA-core SpMM at this density is bound by SM-local operand bandwidth (one "
-                                 "distinct B element per FMA through shared memory), not HBM: see DESIGN.md"},
+                                 "distinct B element per FMA), not HBM; smem_operand_bw = all B reads through LDS at 128 B/clk/SM, "
+                                 "which the dual-path kernel (CSR 5) undercuts by serving part of them from tensor memory: see DESIGN.md"},
             "e2e": e2e,
             "clocks": clocks,
         }

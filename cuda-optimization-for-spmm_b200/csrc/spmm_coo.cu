@@ -16,7 +16,7 @@ namespace cuspmm_b200 {
 int spmm_csr_dispatch(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, uint32_t,
                       const float *, uint32_t, size_t, float *, size_t, int, cudaStream_t);
 int coo_to_csr_rowptrs(const uint32_t *rowIdxs, uint32_t M, uint32_t nnz, uint32_t *rowPtrs, cudaStream_t st);
-int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok);
+int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok, bool sell = false);
 
 // first index i in [from, nnz] whose row is > `row` (i.e. the start of the next row)
 __device__ __forceinline__ uint32_t next_row_start(const uint32_t *__restrict__ rowIdxs, uint32_t nnz,

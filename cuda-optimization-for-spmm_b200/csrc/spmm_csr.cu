@@ -492,7 +492,7 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
 template <bool SELL>
 int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                    const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
-int tmem_rows_per_cta();
+void tmem_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_per_cta);
 
 // =============================================================== host dispatch
 static bool vec_ok(const float *B, size_t ldb, const float *C, size_t ldc, uint32_t N) {
@@ -511,19 +511,27 @@ static uint32_t pick_warps(uint32_t M) {
 //   - no 128-bit loads possible                       -> scalar row-split (4)
 //   - N % 512 == 0, M >= 1024 and each staged B row is re-used often enough by a 60-row panel
 //     (density * 60 >= 1.6, i.e. >= ~2.7 % dense)     -> staged (3): B tiles through shared memory
-//     ... and density >= 12 % with a full wave of CTAs -> dual-path staged (5): part of every B chunk in tensor memory
+//     ... and >= 5.5 non-zeros per staged B row and CTA  -> dual-path staged (5): part of every B chunk in tensor memory
 //   - N <= 512, or short rows (< 96 nnz/row)          -> sub-warp per row (2): 64-column tiles, many rows in flight
 //   - otherwise (wide N, long rows)                   -> warp per row, nnz-balanced (1): A is re-read N/512 times only
-int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok) {
+int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok, bool sell) {
     if (!vec_ok) return 4;
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
     if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 1.6) {
-        // staged; from ~12 % density on (15 % when the column tile is narrower than B, i.e. row-wise TMA copies), with at
-        // least one full wave of CTAs, the dual-path kernel (5) is faster: its TMEM round trip needs long enough chunks to
-        // hide behind (d = 0.10: -6 % .. +20 % depending on the shape; d = 0.12 .. 0.5: 4 .. 32 % faster; spmm_csr_tmem.cu)
-        const uint64_t ctas = (uint64_t)((M + tmem_rows_per_cta() - 1) / tmem_rows_per_cta()) * (N / 512);
-        return (density >= (N == 512 ? 0.12 : 0.15) && ctas >= (uint64_t)sm_count()) ? 5 : 3;
+        // staged.  The dual-path kernel (5) is faster when a CTA's panel re-uses every staged B row often enough for the
+        // chunk to outlast the TMEM copy round trip: rows per CTA x density >= 5.5 non-zeros per B row (8 when the column
+        // tile is narrower than B, i.e. row-wise TMA copies), with at least one full wave of CTAs.  Measured (spmm_csr_tmem.cu,
+        // profiles/r01_sweep.jsonl): 25605^2 d=0.10 (5.8) +6 %, 20000^2 d=0.10 (4.6) -3 %, d=0.12 (5.5) +4 %, d=0.3..0.5 +28..32 %;
+        // N=4096: 11008x4096 d=0.10 (5.5) -20 %, d=0.15 (8.3) +1 %, d=0.5 +28 %
+        uint64_t ctas = 0;
+        uint32_t rpc = 0;
+        tmem_planned_grid(M, N, &ctas, &rpc);
+        const double reuse = (double)rpc * density;
+        // (on the sliced-ELL layout the staged kernel is slower to begin with, so the switch comes earlier: 4.5; with less than a
+        //  wave of CTAs the dual path still wins from ~15 non-zeros per B row: 4000^2 N=512 d=0.3 +5 %, d=0.5 +5..10 %)
+        const double need = N == 512 ? (sell ? 4.5 : 5.5) : 8.0;
+        return ((ctas >= (uint64_t)sm_count() && reuse >= need) || reuse >= 15.0) ? 5 : 3;
     }
     if (N <= 512 || per_row < 96.0) return 2;
     return 1;
@@ -541,7 +549,7 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
     CUSPMM_REQUIRE(rowPtrs && B && C && (nnz == 0 || (colIdxs && vals)), "null operand pointer");
     const bool vok = vec_ok(B, ldb, C, ldc, N);
 
-    if (variant == 0) variant = csr_select_variant(M, K, nnz, N, vok);
+    if (variant == 0) variant = csr_select_variant(M, K, nnz, N, vok, SELL);
 
     // variants 1 and 2 keep their work decomposition but fall back to 32-bit loads when N, ldb/ldc or
     // the base pointers rule out 128-bit ones (N = 21 in data/small_210); variant 4 forces that path

@@ -644,8 +644,13 @@ static int launch_dual(const uint32_t *rowPtrs, const uint32_t *colIdxs, const f
 } // namespace tmemk
 
 // variant 5 of the row kernels (CSR and sliced ELL): N % 512 == 0, 16-byte aligned B/C
-// rows per CTA of the dual-path kernel (29 consumer warps x 2 rows): the selector wants at least one full wave of CTAs
-int tmem_rows_per_cta() { return tmemk::DualCfg<29, 3, 10, 3>::kRows; }
+// the grid the dual-path kernel (29 consumer warps x 2 rows) would use: CTAs and rows per CTA, for the selector
+void tmem_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_per_cta) {
+    const uint32_t ytiles = N / tmemk::kNT;
+    const tmemk::GridPlan g = tmemk::plan_grid(M, ytiles ? ytiles : 1, tmemk::DualCfg<29, 3, 10, 3>::kRows);
+    *ctas = (uint64_t)g.panels * ytiles;
+    *rows_per_cta = g.rpc;
+}
 
 template <bool SELL>
 int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
