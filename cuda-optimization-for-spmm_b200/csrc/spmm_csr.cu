@@ -464,6 +464,8 @@ template <bool SELL>
 int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                 const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
     static const int forceNT = getenv("CUSPMM_STAGED_NT") ? atoi(getenv("CUSPMM_STAGED_NT")) : 0;   // tuning hook
+    // (31 warps x 2 rows on 256- or 128-column tiles, to give the CTAs of a 4096^2 matrix full row slots, measured slower than
+    //  148 half-filled 512-column CTAs: 0.159 / 0.290 ms against 0.136 ms)
     if (forceNT == 128) return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (forceNT == 256 && N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (N % 512 == 0) {
@@ -533,6 +535,9 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
         const double need = N == 512 ? (sell ? 4.5 : 5.5) : 8.0;
         return ((ctas >= (uint64_t)sm_count() && reuse >= need) || reuse >= 15.0) ? 5 : 3;
     }
+    // very short rows: the nnz-balanced warp-per-row kernel wins once a row spans several 64-column tiles of the sub-warp
+    // kernel (20000^2, 14 nnz/row, N=512: 0.047 vs 0.055 ms; 4000^2, 40 nnz/row, N=2048: 0.082 vs 0.087 ms)
+    if ((N >= 1024 && per_row < 96.0) || (N >= 512 && per_row < 24.0)) return 1;
     if (N <= 512 || per_row < 96.0) return 2;
     return 1;
 }
