@@ -1,26 +1,24 @@
-// spmm_csr_tmem.cu -- CSR / sliced-ELL SpMM with the B operand staged in TENSOR MEMORY (variant 5).
+// spmm_csr_tmem.cu -- CSR / sliced-ELL SpMM with TENSOR MEMORY as a second operand port (CSR variant 5, ELL variant 4).
 //
-// The staged kernel (variant 3, spmm_csr.cu) is bound by the shared-memory data pipe: every non-zero
-// needs its own row of B, 4 x LDS.128 per warp for 512 columns = 16 wavefronts at 128 B/clk/SM
-// (measured 17.6 clk per non-zero, profiles/r01_tmem_microbench.txt).  Blackwell has a second on-chip
-// operand store with its own read port: tensor memory (256 KB/SM, 128 lanes x 512 columns).  One
-// tcgen05.ld.32x32b.x16 hands every lane 16 consecutive columns of its TMEM lane -- 2 KB per warp
-// instruction, measured 3.2 clk/SM (641 B/clk/SM, 5x the shared-memory pipe) -- and its column
-// address is a run-time value, so it can be the gathered B row of a non-zero.  No tensor-core MMA is
-// involved: the arithmetic stays fp32 FMA in CSR order (bit-identical to variants 1..4), TMEM is
-// used purely as a faster operand cache ("CSR/COO/ELL are not treated as dense contractions").
+// The staged kernel (variant 3, spmm_csr.cu) is bound by the shared-memory data pipe: every non-zero needs its own row
+// of B, 4 x LDS.128 per warp for 512 columns = 16 wavefronts at 128 B/clk/SM (measured 17.6 clk per non-zero,
+// profiles/r01_tmem_microbench.txt; ncu: pipe 94 % busy).  Blackwell has a second on-chip operand store with its own
+// read port: tensor memory (256 KB/SM, 128 lanes x 512 columns).  One tcgen05.ld.32x32b.x16 hands every lane 16
+// consecutive columns of its TMEM lane -- 2 KB per warp instruction, measured 3.2 clk/SM (641 B/clk/SM, 5x the
+// shared-memory pipe) -- and its column address is a run-time value, so it can be the gathered B row of a non-zero.
+// No tensor-core MMA is involved: the arithmetic stays fp32 FMA in CSR order (bit-identical to variants 1..4); TMEM
+// is used purely as a faster operand cache ("CSR/COO/ELL are not treated as dense contractions").
 //
-// Data path per K-chunk of 16 rows of B (x 512 columns):
-//   L2 --TMA bulk copy--> shared memory ring (SST stages of 32 KB)
-//      --tcgen05.cp.32x128b.warpx4--> TMEM stage (2 stages x 16 rows x 16 columns = all 512 columns)
-//      --tcgen05.ld.32x32b.x16--> registers of the consumer warps
-// TMEM layout: row kk of the chunk occupies columns [16 kk, 16 kk + 16) of EVERY lane quarter
-// (a warp can only read the quarter (warp % 4)): lane l, column 16 kk + 4 u + j  =  B[k0 + kk][128 u + 4 l + j],
-// so lane l ends up with the same four float4 it would have fetched with LDS.128 in variant 3.  The
-// .warpx4 copy shape replicates a 512-byte piece of a B row (32 lanes x 16 B) into all four quarters.
+// TMEM layout: a B row of 512 columns occupies 16 TMEM columns of EVERY lane quarter (a warp can only read the
+// quarter (warp % 4)): lane l, column 16 kk + 4 u + j  =  B[k0 + kk][128 u + 4 l + j], so lane l ends up with the same
+// four float4 it would have fetched with LDS.128.  It is filled from the shared-memory stage by
+// tcgen05.cp.32x128b.warpx4, which replicates a 512-byte piece of a B row (32 lanes x 16 B) into all four quarters;
+// the replication caps TMEM at 32 rows of B.
 //
-// Warp roles (992 threads): warps 0..21 consumers (2 rows of A each, register window of 32 (col, val)
-// entries per row as in variant 3), warp 22 TMA producer, warps 23..30 copy issuers (23 also allocates TMEM).
+// History (git 0c1fac0, profiles/r01_tmem_microbench.txt): a kernel that served EVERY non-zero from TMEM (2 x 16-row
+// TMEM ring behind a shared-memory staging ring, 22 consumer + 8 copy-issuing warps) was bit-exact but slower than
+// variant 3 (5.9 vs 4.33 ms on large_25605): 32 rows are too few to decouple the consumer warps from the copy round
+// trip.  The kernel below keeps variant 3's pipeline and uses TMEM for part of every chunk instead.
 #include "common.cuh"
 
 #include <stdlib.h>
@@ -96,224 +94,7 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t taddr, uint32_t (&v)[16]
         : "r"(taddr)
         : "memory");
 }
-// packed fp32x2 FMA (FFMA2): per component the same IEEE fma as fmaf(), half the issue slots
-__device__ __forceinline__ void ffma2(unsigned long long &acc, unsigned long long a2, uint32_t b0, uint32_t b1) {
-    unsigned long long b;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "r"(b0), "r"(b1));
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a2), "l"(b));
-}
-
 constexpr int kNT = 512;                    // columns of B/C per CTA = 16 TMEM columns per B row
-// TMEM holds 32 rows of B (x 16 columns, x 4 quarters): KC rows per stage x (32 / KC) stages
-
-// NW consumer warps x RW rows, 1 TMA producer warp, NI copy-issuer warps, SST shared-memory stages.
-// A warp can only have one tcgen05.cp in flight per ~60 clk (measured), while the copy engine moves a 512-byte
-// piece in 8 clk (64 B/clk shared-memory read): 8 issuing warps are needed to keep it busy.
-template <int NW, int RW, int NI, int SST, int KC>
-struct Cfg {
-    static constexpr int kNW = NW, kRW = RW, kNI = NI, kSST = SST, kKC = KC, kTStages = 32 / KC;
-    static constexpr uint32_t kStageBytes = KC * kNT * sizeof(float);
-    static constexpr int kRows = NW * RW;
-    static constexpr int kThreads = (NW + 1 + NI) * 32;
-    static constexpr size_t kSmemBytes = (size_t)kStageBytes * SST + (2 * SST + 2 * kTStages) * sizeof(uint64_t) + 16 + 128;
-};
-
-template <class CFG, bool SELL>
-__global__ void __launch_bounds__(CFG::kThreads, 1)
-csr_tmem_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
-                const float *__restrict__ vals, uint32_t M, uint32_t K, uint32_t rpc,
-                const float *__restrict__ B, size_t ldb, float *__restrict__ C, size_t ldc) {
-    constexpr int NW = CFG::kNW, RW = CFG::kRW, NI = CFG::kNI, SST = CFG::kSST, KC = CFG::kKC, NT = kNT;
-    constexpr int kTStages = CFG::kTStages;
-    constexpr uint32_t kStageBytes = CFG::kStageBytes;
-    static_assert((KC * 4) % NI == 0, "the 64 pieces of a chunk are dealt evenly to the issuers");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);
-    uint64_t *full_s = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStageBytes * SST);   // TMA -> copy issuer
-    uint64_t *empty_s = full_s + SST;                                                         // copies done -> TMA
-    uint64_t *full_t = empty_s + SST;                                                         // copies done -> consumers
-    uint64_t *empty_t = full_t + kTStages;                                                    // consumers -> copy issuer
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(empty_t + kTStages);
-
-    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0), lane = lane_id();
-    const uint32_t col0 = blockIdx.y * NT;
-    const uint32_t row0 = blockIdx.x * rpc;
-    const uint32_t rowEnd = min(M, row0 + rpc);
-    const uint32_t nchunks = (K + KC - 1) / KC;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < SST; ++s) { mbar_init(full_s + s, 1); mbar_init(empty_s + s, NI); }
-        for (int s = 0; s < kTStages; ++s) { mbar_init(full_t + s, NI); mbar_init(empty_t + s, NW); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == NW + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == NW) {
-        // ------------------------------------------------------------ TMA producer: B chunk -> shared memory
-        for (uint32_t ch = 0; ch < nchunks; ++ch) {
-            const uint32_t s = ch % SST, it = ch / SST;
-            if (it > 0) mbar_wait(empty_s + s, (it - 1) & 1);
-            const uint32_t k0 = ch * KC;
-            const uint32_t rows = min((uint32_t)KC, K - k0);
-            float *dst = tiles + (size_t)s * KC * NT;
-            if (lane == 0) mbar_expect_tx(full_s + s, rows * NT * (uint32_t)sizeof(float));
-            __syncwarp();
-            if ((size_t)NT == ldb) {
-                if (lane == 0) bulk_g2s(dst, B + (size_t)k0 * ldb + col0, rows * NT * (uint32_t)sizeof(float), full_s + s);
-            } else if (lane < rows) {
-                bulk_g2s(dst + (size_t)lane * NT, B + (size_t)(k0 + lane) * ldb + col0, NT * (uint32_t)sizeof(float), full_s + s);
-            }
-        }
-    } else if (warp > NW) {
-        // ------------------------------------------------------------ copy issuers: shared memory -> TMEM
-        if (lane == 0) {
-            const uint32_t j = warp - (NW + 1);
-            for (uint32_t ch = 0; ch < nchunks; ++ch) {
-                const uint32_t s = ch % SST, ts = ch % kTStages;
-                mbar_wait(full_s + s, (ch / SST) & 1);
-                if (ch >= kTStages) mbar_wait(empty_t + ts, ((ch / kTStages) - 1) & 1);
-                tc_fence_after();
-                const uint64_t desc0 = make_desc(smem_u32(tiles + (size_t)s * KC * NT));
-                const uint32_t t0 = tmem_base + ts * (KC * 16);
-#pragma unroll
-                for (uint32_t p = j; p < KC * 4; p += NI)   // piece p = 512 bytes: row p/4, columns 128 (p%4) ..
-                    tmem_cp_32x128b_x4(t0 + p * 4, desc0 + (uint64_t)(p * 32));
-                tc_commit(empty_s + s);       // the shared-memory stage may be refilled
-                tc_commit(full_t + ts);       // the TMEM stage may be read
-            }
-        }
-    } else {
-        // ------------------------------------------------------------ consumers
-        uint32_t wbase[RW], wj[RW], end[RW], bcol[RW], off[RW];
-        float bval[RW];
-        unsigned long long acc[RW][8];         // acc[i][2u + h] = columns 128u + 4 lane + 2h, +1 (packed fp32x2)
-        auto refill = [&](int i, uint32_t from) {
-            wbase[i] = from;
-            wj[i] = 0;
-            bcol[i] = kPad;
-            bval[i] = 0.f;
-            if (from + lane < end[i]) {
-                const size_t at = SELL ? (size_t)off[i] + (size_t)(from + lane) * 32u : (size_t)(from + lane);
-                bcol[i] = ld_stream(colIdxs + at);
-                bval[i] = ld_stream(vals + at);
-            }
-        };
-#pragma unroll
-        for (int i = 0; i < RW; ++i) {
-            const uint32_t r = row0 + warp * RW + i;
-            uint32_t p0 = 0;
-            end[i] = 0;
-            off[i] = 0;
-            if (r < rowEnd) {
-                if constexpr (SELL) {
-                    const uint32_t sb = __ldg(rowPtrs + (r >> 5));
-                    off[i] = sb + (r & 31u);
-                    end[i] = (__ldg(rowPtrs + (r >> 5) + 1) - sb) >> 5;
-                } else {
-                    p0 = __ldg(rowPtrs + r);
-                    end[i] = __ldg(rowPtrs + r + 1);
-                }
-            }
-            p0 = __shfl_sync(0xFFFFFFFFu, p0, 0);
-            end[i] = __shfl_sync(0xFFFFFFFFu, end[i], 0);
-            off[i] = __shfl_sync(0xFFFFFFFFu, off[i], 0);
-            refill(i, p0);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[i][e] = 0ull;
-        }
-        const uint32_t tq = tmem_base + (((warp & 3u) * 32u) << 16);     // this warp's lane quarter
-
-        auto consume = [&](int i, uint32_t cbase, uint32_t c, float v) {
-            uint32_t b[16];
-            tmem_ld16_wait(cbase + (c << 4), b);
-            unsigned long long v2;
-            asm("mov.b64 %0, {%1, %1};" : "=l"(v2) : "r"(__float_as_uint(v)));
-#pragma unroll
-            for (int e = 0; e < 8; ++e) ffma2(acc[i][e], v2, b[2 * e], b[2 * e + 1]);
-        };
-
-        for (uint32_t ch = 0; ch < nchunks; ++ch) {
-            const uint32_t ts = ch % kTStages;
-            const uint32_t k0 = ch * KC, k1 = k0 + KC;
-            uint32_t nn[RW], maxn = 0;
-#pragma unroll
-            for (int i = 0; i < RW; ++i) {
-                // window columns are ascending and the consumed ones are a prefix below k0
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, bcol[i] < k1);
-                nn[i] = __popc(m) - wj[i];
-                maxn = max(maxn, nn[i]);
-            }
-            mbar_wait(full_t + ts, (ch / kTStages) & 1);
-            tc_fence_after();
-            // TMEM column of B row c:  stage base + 16 (c - k0)   (mod 2^32 arithmetic)
-            const uint32_t cbase = tq + ts * (KC * 16) - (k0 << 4);
-            for (uint32_t t = 0; t < maxn; ++t) {
-#pragma unroll
-                for (int i = 0; i < RW; ++i) {
-                    if (t < nn[i]) {
-                        const uint32_t c = __shfl_sync(0xFFFFFFFFu, bcol[i], wj[i] + t);
-                        const float v = __shfl_sync(0xFFFFFFFFu, bval[i], wj[i] + t);
-                        consume(i, cbase, c, v);
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < RW; ++i) {
-                wj[i] += nn[i];
-                // window used up while the row may still have entries inside this chunk: refill and
-                // finish the chunk entry by entry
-                if (wj[i] == 32 && wbase[i] + 32 < end[i]) {
-                    refill(i, wbase[i] + 32);
-                    while (true) {
-                        if (wj[i] == 32) {
-                            if (wbase[i] + 32 >= end[i]) break;
-                            refill(i, wbase[i] + 32);
-                        }
-                        const uint32_t c = __shfl_sync(0xFFFFFFFFu, bcol[i], wj[i]);
-                        if (c >= k1) break;                  // also ends at the row end (kPad)
-                        const float v = __shfl_sync(0xFFFFFFFFu, bval[i], wj[i]);
-                        consume(i, cbase, c, v);
-                        ++wj[i];
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_t + ts);
-        }
-
-#pragma unroll
-        for (int i = 0; i < RW; ++i) {
-            const uint32_t r = row0 + warp * RW + i;
-            if (r < rowEnd) {
-                float4 *crow = reinterpret_cast<float4 *>(C + (size_t)r * ldc + col0) + lane;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    float4 o;
-                    o.x = __uint_as_float((uint32_t)acc[i][2 * u]);
-                    o.y = __uint_as_float((uint32_t)(acc[i][2 * u] >> 32));
-                    o.z = __uint_as_float((uint32_t)acc[i][2 * u + 1]);
-                    o.w = __uint_as_float((uint32_t)(acc[i][2 * u + 1] >> 32));
-                    __stcs(crow + u * 32, o);
-                }
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == NW + 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
 
 // whole waves of the SM count, rows per CTA = ceil(M / panels) <= rowSlots (as the staged kernel)
 struct GridPlan { uint32_t panels, rpc; };
@@ -329,25 +110,6 @@ static GridPlan plan_grid(uint32_t M, uint32_t ytiles, uint32_t rowSlots) {
     if (g.rpc == 0) g.rpc = 1;
     g.panels = (M + g.rpc - 1) / g.rpc;
     return g;
-}
-
-template <class CFG, bool SELL>
-static int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
-                  const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
-    auto kern = csr_tmem_kernel<CFG, SELL>;
-    static bool attr_done[64] = {};
-    int dev = 0;
-    CUSPMM_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
-        CUSPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::kSmemBytes));
-        attr_done[dev & 63] = true;
-    }
-    const uint32_t ytiles = N / kNT;
-    const GridPlan g = plan_grid(M, ytiles, CFG::kRows);
-    dim3 grid(g.panels, ytiles);
-    kern<<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(rowPtrs, colIdxs, vals, M, K, g.rpc, B, ldb, C, ldc);
-    CUSPMM_LAUNCH_CHECK("csr_tmem_kernel");
-    return CUSPMM_OK;
 }
 
 
@@ -658,9 +420,6 @@ int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float
     if (N % tmemk::kNT != 0)
         return set_error(CUSPMM_ERR_UNSUPPORTED, "TMEM-staged kernel needs N %% 512 == 0 (N=%u)", N);
     static const int shape = getenv("CUSPMM_TMEM_SHAPE") ? atoi(getenv("CUSPMM_TMEM_SHAPE")) : 0;   // tuning hook
-    // 10..12: the pure TMEM-staged kernel (kept for the record: slower, see profiles/r01_tmem_microbench.txt)
-    if (shape == 10) return tmemk::launch<tmemk::Cfg<22, 2, 8, 6, 16>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    if (shape == 11) return tmemk::launch<tmemk::Cfg<22, 2, 8, 12, 8>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     // dual operand path: consumers, issuers, TMEM rows per chunk, TMEM stages  (large_25605: 10 rows x 3 stages 4.11 ms,
     // 8 x 3: 4.16, 6 x 3: 4.25, 4 x 3: 4.36, 1 x 3: 4.52, 16 x 2: 4.51; variant 3: 4.33)
     if (shape == 3) return tmemk::launch_dual<tmemk::DualCfg<30, 2, 10, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
