@@ -62,7 +62,27 @@ __global__ void coo_rowptr_kernel(const uint32_t *__restrict__ rowIdxs, uint32_t
     for (int64_t r = prev + 1; r <= cur; ++r) rowPtrs[r] = (uint32_t)i;
 }
 
+// The same pointers by M + 1 independent binary searches over the sorted row indices: ~log2(nnz) dependent loads per row
+// instead of streaming all of rowIdxs (25605^2 at 10 %: 0.7 M probes against 262 MB; 0.17 ms -> ~0.02 ms).
+__global__ void coo_rowptr_search_kernel(const uint32_t *__restrict__ rowIdxs, uint32_t M, uint32_t nnz,
+                                         uint32_t *__restrict__ rowPtrs) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > M) return;
+    uint32_t lo = 0, hi = nnz;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(rowIdxs + mid) < r) lo = mid + 1;
+        else hi = mid;
+    }
+    rowPtrs[r] = lo;
+}
+
 int coo_to_csr_rowptrs(const uint32_t *rowIdxs, uint32_t M, uint32_t nnz, uint32_t *rowPtrs, cudaStream_t st) {
+    if ((uint64_t)nnz >= 64ull * ((uint64_t)M + 1)) {     // long rows: searching is cheaper than streaming
+        coo_rowptr_search_kernel<<<(M + 1 + 127) / 128, 128, 0, st>>>(rowIdxs, M, nnz, rowPtrs);
+        CUSPMM_LAUNCH_CHECK("coo_rowptr_search_kernel");
+        return CUSPMM_OK;
+    }
     const uint64_t n = (uint64_t)nnz + 1;
     coo_rowptr_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowIdxs, M, nnz, rowPtrs);
     CUSPMM_LAUNCH_CHECK("coo_rowptr_kernel");

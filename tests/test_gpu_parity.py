@@ -263,7 +263,7 @@ def test_bsr_rectangular_blocks(b):
 
 
 # ------------------------------------------------------------------ device converters, bit-exact
-@pytest.mark.parametrize("M,K,d,skew", [(1, 1, 1.0, False), (31, 40, 0.2, False), (32, 40, 0.2, False),
+@pytest.mark.parametrize("M,K,d,skew", [(1, 1, 1.0, False), (31, 40, 0.2, False), (32, 40, 0.2, False), (70, 900, 0.3, False),
                                         (1000, 800, 0.03, True), (4097, 300, 0.05, False), (100, 100, 0.0, False)])
 def test_device_conversions_bit_exact(b, M, K, d, skew):
     a = random_csr(M, K, d, seed=M + K, skew=skew)
