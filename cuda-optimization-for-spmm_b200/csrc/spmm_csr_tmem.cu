@@ -125,15 +125,16 @@ static GridPlan plan_grid(uint32_t M, uint32_t ytiles, uint32_t rowSlots) {
 // Warps: 0..NW-1 consumers, NW..NW+NI-1 copy issuers; issuer 0 also drives the TMA ring.
 // (Tried and dropped: keeping the TMEM rows out of the ring -- a separate double buffer for them and a 4..5-deep
 //  ring of the other rows -- measured 4.22 ms against 4.11 ms for this version on large_25605.)
-template <int NW, int NI, int TR, int TS>
+template <int NW, int NI, int TR, int TS, int KC = 32, int STAGES = 3>
 struct DualCfg {
-    static constexpr int kNW = NW, kNI = NI, kTR = TR, kTS = TS, kRW = 2, kKC = 32, kStages = 3;
-    static_assert(TR * TS * 16 <= 512 && TR >= 1 && TR <= 32 && TS <= kStages, "TMEM has 512 columns; a TMEM stage lives as long as its ring stage");
+    static constexpr int kNW = NW, kNI = NI, kTR = TR, kTS = TS, kRW = 2, kKC = KC, kStages = STAGES;
+    static_assert(TR * TS * 16 <= 512 && TR >= 1 && TR <= KC && KC <= 32 && TS <= kStages, "TMEM has 512 columns; a TMEM stage lives as long as its ring stage");
     static constexpr int kRows = NW * kRW;
     static constexpr int kThreads = (NW + NI) * 32;
     static constexpr uint32_t kRowBytes = kNT * sizeof(float);                  // 2 KB
     static constexpr uint32_t kStageBytes = kKC * kRowBytes;                    // 64 KB
     static constexpr size_t kSmemBytes = (size_t)kStageBytes * kStages + 3 * kStages * sizeof(uint64_t) + 16 + 128;
+    static_assert(kSmemBytes <= 232448, "more than 227 KB of shared memory");
 };
 
 template <class CFG, bool SELL>
@@ -422,14 +423,14 @@ int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float
     static const int shape = getenv("CUSPMM_TMEM_SHAPE") ? atoi(getenv("CUSPMM_TMEM_SHAPE")) : 0;   // tuning hook
     // dual operand path: consumers, issuers, TMEM rows per chunk, TMEM stages  (large_25605: 10 rows x 3 stages 4.11 ms,
     // 8 x 3: 4.16, 6 x 3: 4.25, 4 x 3: 4.36, 1 x 3: 4.52, 16 x 2: 4.51; variant 3: 4.33)
-    if (shape == 3) return tmemk::launch_dual<tmemk::DualCfg<30, 2, 10, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    if (shape == 4) return tmemk::launch_dual<tmemk::DualCfg<29, 3, 8, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    // (also measured on large_25605, d = 0.10: 24-row chunks x 4 ring stages 4.20 ms, 20-row chunks x 4 stages 4.71 ms, 30 consumer +
+    //  2 issuer warps 4.39 ms -- the per-chunk bookkeeping outweighs the deeper ring / the larger TMEM share)
     // TMEM rows per chunk by density (large_25605, ms):   d     0.10   0.15   0.2    0.3    0.5
     //   the longer a chunk keeps the consumers busy,       v3     4.33   6.40   8.48   12.65  21.0
     //   the better a 2-deep TMEM ring of 16 rows hides     10x3   4.16   5.60   7.15   10.28  16.67
     //   its refill round trip                              16x2   4.51   5.89   7.10   9.68   15.11
     const double density = (double)nnz / ((double)M * (double)K);
-    if (shape == 1 || (shape == 0 && density < 0.2))
+    if (shape == 1 || (shape != 2 && density < 0.2))
         return tmemk::launch_dual<tmemk::DualCfg<29, 3, 10, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     return tmemk::launch_dual<tmemk::DualCfg<29, 3, 16, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
 }
