@@ -36,6 +36,9 @@ def lib():
         L.cuspmm_spmm_coo_workspace.restype = SZ
         L.cuspmm_spmm_coo_workspace.argtypes = [U32, U32, U32, C.c_int]
         L.cuspmm_spmm_csr.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P]
+        L.cuspmm_spmm_csr_workspace.restype = SZ
+        L.cuspmm_spmm_csr_workspace.argtypes = [U32, U32, U32, U32, C.c_int]
+        L.cuspmm_spmm_csr_ws.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P, SZ, P]
         L.cuspmm_spmm_coo.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P, SZ, P]
         L.cuspmm_spmm_sell.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P]
         L.cuspmm_spmm_bsr_f32.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, SZ, P, SZ, P]
@@ -105,13 +108,30 @@ def _ptr(t):
 
 
 # ------------------------------------------------------------------------------- SpMM
-def spmm_csr(rowPtrs, colIdxs, vals, M, K, B, variant=0, out=None, nnz=None):
+_CSR_WS = {}
+
+
+def spmm_csr(rowPtrs, colIdxs, vals, M, K, B, variant=0, out=None, nnz=None, allow_split=False):
+    """variant 0 through cuspmm_spmm_csr keeps the all-variants-bit-identical order; allow_split=True goes through
+    cuspmm_spmm_csr_ws, whose selector may pick the row-cutting kernel (variant 6) for few / skewed rows."""
     torch = _torch()
     N = B.shape[1]
     Cm = out if out is not None else torch.empty((M, N), dtype=torch.float32, device=B.device)
     nnz = int(colIdxs.numel()) if nnz is None else nnz
-    check(lib().cuspmm_spmm_csr(_ptr(rowPtrs), _ptr(colIdxs), _ptr(vals), M, K, nnz, _ptr(B), N, B.stride(0),
-                                _ptr(Cm), Cm.stride(0), variant, _stream()), f"cuspmm_spmm_csr(variant={variant})")
+    wsb = lib().cuspmm_spmm_csr_workspace(M, K, nnz, N, variant) if (variant == 6 or allow_split) else 0
+    if wsb == 0:
+        check(lib().cuspmm_spmm_csr(_ptr(rowPtrs), _ptr(colIdxs), _ptr(vals), M, K, nnz, _ptr(B), N, B.stride(0),
+                                    _ptr(Cm), Cm.stride(0), variant, _stream()), f"cuspmm_spmm_csr(variant={variant})")
+        return Cm
+    # variant 6 (or the selector may want it): caller-provided workspace, kept per (device, size) between calls
+    key = (B.device.index, wsb)
+    ws = _CSR_WS.get(key)
+    if ws is None:
+        _CSR_WS.clear()
+        ws = _CSR_WS[key] = torch.empty(wsb, dtype=torch.uint8, device=B.device)
+    check(lib().cuspmm_spmm_csr_ws(_ptr(rowPtrs), _ptr(colIdxs), _ptr(vals), M, K, nnz, _ptr(B), N, B.stride(0),
+                                   _ptr(Cm), Cm.stride(0), variant, _ptr(ws), wsb, _stream()),
+          f"cuspmm_spmm_csr_ws(variant={variant})")
     return Cm
 
 

@@ -495,6 +495,10 @@ template <bool SELL>
 int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                    const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
 void tmem_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_per_cta);
+// variant 6: nnz split that cuts rows, ordered carry fix-up (spmm_csr_split.cu); needs workspace
+size_t spmm_csr_split_workspace(uint32_t nnz, uint32_t N);
+int spmm_csr_split(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
+                   const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, void *ws, size_t wsBytes, cudaStream_t st);
 
 // =============================================================== host dispatch
 static bool vec_ok(const float *B, size_t ldb, const float *C, size_t ldc, uint32_t N) {
@@ -566,16 +570,17 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
 
     switch (variant) {
     case 1: {
-        if (N > 256) {
-            dim3 grid(blocks, (N + 511) / 512);
-            csr_rowsplit_vec_kernel<4, 2, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
-        } else if (N > 128) {
-            dim3 grid(blocks, 1);
-            csr_rowsplit_vec_kernel<2, 4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
-        } else {
-            dim3 grid(blocks, 1);
-            csr_rowsplit_vec_kernel<1, 8, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
-        }
+        // column tile per warp: 512 columns (4 float4 per lane) re-read A least; few rows (or a forced tile) -> narrower tiles,
+        // so that a long row's entries are spread over several warps and more B rows are in flight per row
+        static const int forceU = getenv("CUSPMM_ROWSPLIT_U") ? atoi(getenv("CUSPMM_ROWSPLIT_U")) : 0;   // tuning hook
+        int U = N > 256 ? 4 : (N > 128 ? 2 : 1);
+        if (forceU == 1 || forceU == 2 || forceU == 4) U = forceU;
+        const dim3 grid(blocks, (N + 128u * U - 1) / (128u * U));
+        if (U == 4) csr_rowsplit_vec_kernel<4, 2, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        else if (U == 2) csr_rowsplit_vec_kernel<2, 4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        else if (forceU == 1 && getenv("CUSPMM_ROWSPLIT_J16"))
+            csr_rowsplit_vec_kernel<1, 16, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
+        else csr_rowsplit_vec_kernel<1, 8, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         CUSPMM_LAUNCH_CHECK("csr_rowsplit_vec_kernel");
         return CUSPMM_OK;
     }
@@ -599,6 +604,8 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
             return set_error(CUSPMM_ERR_UNSUPPORTED, "TMEM-staged kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
         return spmm_rows_tmem<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
     }
+    case 6:
+        return set_error(CUSPMM_ERR_WORKSPACE, "CSR variant 6 needs workspace: call cuspmm_spmm_csr_ws (cuspmm_spmm_csr_workspace bytes)");
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);
         csr_rowsplit_scalar_kernel<4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
@@ -615,6 +622,36 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
     return rows_dispatch<false>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, variant, st);
 }
 
+// Few rows with enough non-zeros each: whole rows per warp leave the machine idle and the longest row is the critical path
+// (GL7d25, 2798 rows of 2..422 non-zeros, N = 512: 0.072 ms; cut into equal nnz ranges: see profiles/r01_real_matrices.jsonl).
+static bool prefer_split(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vok) {
+    if (!vok || M == 0) return false;
+    if (csr_select_variant(M, K, nnz, N, vok, false) == 3 || csr_select_variant(M, K, nnz, N, vok, false) == 5) return false;
+    const uint64_t rowWarps = (uint64_t)M * ((N + 511) / 512);
+    return rowWarps < (uint64_t)sm_count() * 32 && (double)nnz / M >= 16.0;
+}
+
+size_t spmm_csr_workspace_bytes(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int variant) {
+    if (variant == 6) return spmm_csr_split_workspace(nnz, N);
+    if (variant == 0 && prefer_split(M, K, nnz, N, N % 4 == 0)) return spmm_csr_split_workspace(nnz, N);
+    return 0;
+}
+
+int spmm_csr_dispatch_ws(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                         uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
+                         float *C, size_t ldc, int variant, void *ws, size_t wsBytes, cudaStream_t st) {
+    CUSPMM_REQUIRE(ldb >= N && ldc >= N, "ldb/ldc (%zu/%zu) must be >= N (%u)", ldb, ldc, N);
+    if (M == 0 || N == 0) return CUSPMM_OK;
+    if (variant == 0 && ws && B && C && prefer_split(M, K, nnz, N, vec_ok(B, ldb, C, ldc, N)) &&
+        wsBytes >= spmm_csr_split_workspace(nnz, N) && (reinterpret_cast<uintptr_t>(ws) & 15) == 0)
+        variant = 6;
+    if (variant == 6) {
+        CUSPMM_REQUIRE(rowPtrs && B && C && (nnz == 0 || (colIdxs && vals)), "null operand pointer");
+        return spmm_csr_split(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, ws, wsBytes, st);
+    }
+    return rows_dispatch<false>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, variant, st);
+}
+
 // the same kernels on a sliced-ELL matrix (called from spmm_ell.cu); variant numbering as CSR
 int spmm_sell_rows_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
                             uint32_t M, uint32_t K, uint32_t slots, const float *B, uint32_t N, size_t ldb,
@@ -623,6 +660,17 @@ int spmm_sell_rows_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, 
 }
 
 } // namespace cuspmm_b200
+
+extern "C" size_t cuspmm_spmm_csr_workspace(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int variant) {
+    return cuspmm_b200::spmm_csr_workspace_bytes(M, K, nnz, N, variant);
+}
+
+extern "C" int cuspmm_spmm_csr_ws(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                                  uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
+                                  float *C, size_t ldc, int variant, void *workspace, size_t workspace_bytes, void *stream) {
+    return cuspmm_b200::spmm_csr_dispatch_ws(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, variant, workspace,
+                                             workspace_bytes, cuspmm_b200::as_stream(stream));
+}
 
 extern "C" int cuspmm_spmm_csr(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
                                uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,

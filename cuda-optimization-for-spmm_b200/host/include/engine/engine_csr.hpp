@@ -27,6 +27,9 @@ DenseMatrix<DT, MT> *spmmCSRWrapper4(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT,
 // additive (the reference stops at 4): the staged kernel with part of every B chunk in tensor memory
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmCSRWrapper5(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+// additive: equal nnz ranges per warp, rows cut at range boundaries, ordered carry fix-up (few / skewed rows)
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmCSRWrapper6(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 
 template <typename DT, typename MT, typename AccT>
 class EngineCSR : public EngineBase {
@@ -40,7 +43,7 @@ class EngineCSR : public EngineBase {
     double seqTime = 1.f;
 
     explicit EngineCSR(std::string dirPath) {
-        this->numKernels = 5;
+        this->numKernels = 6;
         this->dirPath = dirPath;
         this->fmt = "CSR";
     }
@@ -61,6 +64,7 @@ class EngineCSR : public EngineBase {
         if (num == 3) return spmmCSRWrapper3<DT, MT, AccT>(ma, mb, mc);
         if (num == 4) return spmmCSRWrapper4<DT, MT, AccT>(ma, mb, mc);
         if (num == 5) return spmmCSRWrapper5<DT, MT, AccT>(ma, mb, mc);
+        if (num == 6) return spmmCSRWrapper6<DT, MT, AccT>(ma, mb, mc);
         if (num == -1) return spmmCSRWrapper3<DT, MT, AccT>(ma, mb, mc);
         throw std::runtime_error("Not implemented");
     }

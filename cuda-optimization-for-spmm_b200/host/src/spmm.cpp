@@ -178,9 +178,13 @@ static DenseMatrix<DT, MT> *csrWrapper(int k, const char *name, SparseMatrixCSR<
     ks.algBytes = 8.0 * ks.nnz + 4.0 * (ks.M + 1.0) + 4.0 * ks.K * N + 4.0 * ks.M * N;
     ks.flops = 2.0 * ks.nnz * N;
     int probe = CUSPMM_OK;
+    // variant 6 cuts rows between warps and needs carry slots: caller-provided workspace (0 bytes for the other variants)
+    const size_t wsBytes = cuspmm_spmm_csr_workspace(a->numRows, a->numCols, a->numNonZero, b->numCols, k);
+    void *ws = nullptr;
+    if (wsBytes) cudaCheckError(cudaMalloc(&ws, wsBytes));
     auto launch = [&](DenseMatrix<DT, MT> *c) {
-        return cuspmm_spmm_csr(a->rowPtrs, a->colIdxs, a->data, a->numRows, a->numCols, a->numNonZero, b->data, b->numCols,
-                               b->numCols, c->data, c->numCols, k, nullptr);
+        return cuspmm_spmm_csr_ws(a->rowPtrs, a->colIdxs, a->data, a->numRows, a->numCols, a->numNonZero, b->data, b->numCols,
+                                  b->numCols, c->data, c->numCols, k, ws, wsBytes, nullptr);
     };
     // shape support is decided by the library: a dry call into a scratch C tells us (status 1/3 = cannot run)
     auto prolog = [&]() {
@@ -188,7 +192,9 @@ static DenseMatrix<DT, MT> *csrWrapper(int k, const char *name, SparseMatrixCSR<
         probe = launch(&scratch);
         return probe == CUSPMM_OK;
     };
-    return runWrapper<DT, MT>(ks, b, ref, prolog, launch);
+    auto *res = runWrapper<DT, MT>(ks, b, ref, prolog, launch);
+    if (ws) cudaCheckError(cudaFree(ws));
+    return res;
 }
 
 #define CSR_WRAPPER(k, name)                                                                                            \
@@ -201,6 +207,7 @@ CSR_WRAPPER(2, "csr_subwarp_vec")
 CSR_WRAPPER(3, "csr_staged_tma")
 CSR_WRAPPER(4, "csr_rowsplit_scalar")
 CSR_WRAPPER(5, "csr_staged_tma_tmem")
+CSR_WRAPPER(6, "csr_nnz_split_ordered_carry")
 
 // ------------------------------------------------------------------------------- COO wrappers
 template <typename DT, typename MT, typename AccT>
@@ -336,6 +343,7 @@ template Dn *spmmCSRWrapper2<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper3<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper4<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper5<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
+template Dn *spmmCSRWrapper6<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper1<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper2<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmELLWrapper1<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);

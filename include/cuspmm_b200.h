@@ -63,12 +63,23 @@ int cuspmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
  *   5  staged, dual operand path: as 3, and the first rows of every B chunk are copied on
  *      into tensor memory (tcgen05.cp) and gathered from there with tcgen05.ld, which
  *      takes those non-zeros off the shared-memory pipe; fp32 FMA in CSR order like 1..4
- *      (N % 512 == 0, else CUSPMM_ERR_UNSUPPORTED) */
-#define CUSPMM_CSR_NUM_VARIANTS 5
+ *      (N % 512 == 0, else CUSPMM_ERR_UNSUPPORTED)
+ *   6  nnz split that cuts rows between warps (merge-path style) with an ordered carry fix-up, for few / skewed rows;
+ *      no atomics, fixed order; cut rows are rounded differently from 1..5 (partial sums first), uncut rows identically.
+ *      Needs workspace: only through cuspmm_spmm_csr_ws. */
+#define CUSPMM_CSR_NUM_VARIANTS 6
 int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
                     uint32_t M, uint32_t K, uint32_t nnz,
                     const float *B_dev, uint32_t N, size_t ldb,
                     float *C_dev, size_t ldc, int variant, void *stream);
+/* The same with caller-provided device workspace (16-byte aligned, cuspmm_spmm_csr_workspace bytes; 0 for variants
+ * 1..5): variant 6 runs, and variant 0 may select it (few rows with >= 16 non-zeros each). */
+size_t cuspmm_spmm_csr_workspace(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int variant);
+int cuspmm_spmm_csr_ws(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
+                       uint32_t M, uint32_t K, uint32_t nnz,
+                       const float *B_dev, uint32_t N, size_t ldb,
+                       float *C_dev, size_t ldc, int variant,
+                       void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------- COO ---- */
 /* Replaces spmmCOOWrapper1 / spmmCOOK1 (include/engine/engine_coo.hpp:14-15,
