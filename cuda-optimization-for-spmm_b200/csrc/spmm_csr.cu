@@ -14,8 +14,11 @@
 //                                 one producer warp) and re-used by all rows of the panel;
 //                                 31 consumer warps x 2 rows (or 15 x 2 / 15 x 4, see launch_by_N)
 //   variant 4  csr_rowsplit_scalar any N / ldb / alignment (N = 21 in data/small_210)
-//   variant 5  csr_tmem           variant 3's design with the B chunks in tensor memory, read with
-//                                 tcgen05.ld instead of LDS (spmm_csr_tmem.cu)
+//   variant 5  csr_dual           variant 3's pipeline with tensor memory as a second operand port: the first rows of
+//                                 every B chunk are copied into TMEM (tcgen05.cp) and gathered with tcgen05.ld.x16
+//                                 instead of LDS (spmm_csr_tmem.cu)
+//   variant 6  csr_nnzsplit       equal nnz ranges per warp, rows cut at range boundaries, ordered carry fix-up
+//                                 (spmm_csr_split.cu; needs workspace: cuspmm_spmm_csr_ws)
 // All row kernels are templated on the row accessor (RowRef<SELL>), so the same code runs on the
 // sliced-ELL layout (spmm_ell.cu calls spmm_sell_rows_dispatch).
 #include "common.cuh"

@@ -13,6 +13,8 @@
 // Needs 2 * 129 * 4 bytes of caller-provided workspace per (warp, 128-column tile) (cuspmm_spmm_csr_workspace).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace cuspmm_b200 {
 namespace split {
 
@@ -26,12 +28,13 @@ static Plan make_plan(uint32_t nnz, uint32_t N) {
     Plan p;
     p.tiles = (N + 127) / 128;
     const uint64_t maxWarps = (uint64_t)sm_count() * 64 / p.tiles + 1;
-    uint64_t warps = ((uint64_t)nnz + 63) / 64;
+    static const uint32_t minPer = getenv("CUSPMM_SPLIT_PER") ? (uint32_t)atoi(getenv("CUSPMM_SPLIT_PER")) : 64u;   // tuning hook
+    uint64_t warps = ((uint64_t)nnz + minPer - 1) / minPer;
     if (warps > maxWarps) warps = maxWarps;
     if (warps == 0) warps = 1;
     uint64_t per = ((uint64_t)nnz + warps - 1) / warps;
     per = (per + 31) / 32 * 32;
-    if (per < 64) per = 64;
+    if (per < minPer) per = minPer;
     p.perWarp = (uint32_t)per;
     p.warps = (uint32_t)(((uint64_t)nnz + per - 1) / per);
     if (p.warps == 0) p.warps = 1;
