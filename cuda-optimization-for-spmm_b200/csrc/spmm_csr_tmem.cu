@@ -220,7 +220,7 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
                 if (r) { if (lane == 0) cp_issue(cc); ++cc; did = true; }
             }
             if (did) idle = 0;
-            else { __nanosleep(40); if (++idle > (1u << 24)) __trap(); }   // a lost arrive must fail loudly, not hang the GPU
+            else { __nanosleep(64); if (++idle > (1u << 28)) __trap(); }   // ~20 s without progress: a lost arrive must fail loudly, not hang the GPU
         }
     } else {
         // ------------------------------------------------------------ consumers
