@@ -174,6 +174,7 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
     if (warp >= NW) {
         // ------------------------------------------------------------ issuers (issuer 0 = TMA producer too)
         const uint32_t j = warp - NW;
+        const bool rowwise = (size_t)NT != ldb && NI > 1;
         // Two task streams, both driven by non-blocking barrier tests so that neither holds up the other:
         //   TMA load of chunk c (issuer 0):  B rows -> ring stage c % 3, once chunk c - 3 is consumed
         //   copies of chunk c (all issuers): first TR rows of the stage -> TMEM stage c % TS, once the TMA data
@@ -204,8 +205,13 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
             tc_fence_after();
             const uint64_t desc0 = make_desc(smem_u32(ring + (size_t)(c % STAGES) * kStageBytes));
             const uint32_t t0 = tmem_base + (c % TS) * (TR * 16);
-            for (uint32_t p = j; p < TR * 4; p += NI)     // piece p = 512 bytes: row p/4 of the chunk, columns 128 (p%4) ..
-                tmem_cp_32x128b_x4(t0 + p * 4, desc0 + (uint64_t)(p * 32));
+            // piece p = 512 bytes: row p/4 of the chunk, columns 128 (p%4) ..; dealt round-robin to the copying issuers.
+            // When the column tile is narrower than B the TMA load of a chunk is 32 row copies issued by issuer 0's lanes:
+            // that warp then copies nothing (it still commits, so the barrier count stays NI).
+            const uint32_t nCopy = rowwise ? NI - 1 : NI, jj = rowwise ? j - 1 : j;
+            if (!(rowwise && j == 0))
+                for (uint32_t p = jj; p < TR * 4; p += nCopy)
+                    tmem_cp_32x128b_x4(t0 + p * 4, desc0 + (uint64_t)(p * 32));
             tc_commit(full + c % STAGES);
         };
         uint32_t cc = 0, tc = (j == 0) ? 0u : nchunks, idle = 0;
@@ -430,8 +436,12 @@ int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float
     //   the better a 2-deep TMEM ring of 16 rows hides     10x3   4.16   5.60   7.15   10.28  16.67
     //   its refill round trip                              16x2   4.51   5.89   7.10   9.68   15.11
     const double density = (double)nnz / ((double)M * (double)K);
-    if (shape == 1 || (shape != 2 && density < 0.2))
-        return tmemk::launch_dual<tmemk::DualCfg<29, 3, 10, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    const bool sparse = shape == 1 || (shape != 2 && density < 0.2);
+    if ((size_t)tmemk::kNT != ldb) {      // row-wise TMA copies: a fourth issuer warp, issuer 0 only loads (28 consumers)
+        if (sparse) return tmemk::launch_dual<tmemk::DualCfg<28, 4, 10, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+        return tmemk::launch_dual<tmemk::DualCfg<28, 4, 16, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    }
+    if (sparse) return tmemk::launch_dual<tmemk::DualCfg<29, 3, 10, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     return tmemk::launch_dual<tmemk::DualCfg<29, 3, 16, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
 }
 template int spmm_rows_tmem<false>(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, uint64_t,
