@@ -137,6 +137,26 @@ def test_noncontiguous_ldb_ldc(b):
     assert (outbig[:, :32] == 7.0).all().item() and (outbig[:, 128:] == 7.0).all().item()
 
 
+def test_noncontiguous_ldb_ldc_staged_kernels(b):
+    """B and C as column windows of wider buffers (ldb, ldc > N): the TMA ring of variants 3 / 5 copies row by row, the
+    epilogue strides by ldc; the row-cutting kernel (6) likewise.  Nothing outside the window may be written."""
+    import torch
+    M, K, N = 700, 300, 512
+    a = random_csr(M, K, 0.2, seed=15)
+    B = np.random.default_rng(16).uniform(-1, 1, (K, N)).astype(np.float32)
+    big = torch.full((K, N + 256), float("nan"), device="cuda")
+    big[:, 128:128 + N] = b.dev_f32(B)
+    Bv = big[:, 128:128 + N]               # ldb = 768, 16-byte aligned offset
+    ref, den = orc.spmm_csr(a, B, omp=True), orc.absprod_csr(a, B)
+    rp, ci, va = dev_csr(b, a)
+    for variant in (3, 5, 6):
+        outbig = torch.full((M, N + 64), 7.0, device="cuda")
+        out = outbig[:, 32:32 + N]         # ldc = 576
+        b.spmm_csr(rp, ci, va, M, K, Bv, variant=variant, out=out)
+        check(out.contiguous(), ref, den)
+        assert (outbig[:, :32] == 7.0).all().item() and (outbig[:, 32 + N:] == 7.0).all().item()
+
+
 @pytest.mark.parametrize("M,K,N,d", [(2048, 1000, 128, 0.10), (1500, 2051, 256, 0.06), (3000, 1024, 512, 0.05),
                                      (1111, 777, 1024, 0.08)])
 def test_csr_staged_kernel(b, M, K, N, d):
