@@ -292,11 +292,15 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
     const uint32_t rowEnd = min(M, row0 + rpc);
     const uint32_t nchunks = (K + KC - 1) / KC;
 
+    // consumer warps that got no rows (the last panel, or rpc < the CTA's row slots) leave at once: spinning on the
+    // barriers they would steal issue slots from the working warps (4096^2: 14 of 31 warps have rows)
+    const uint32_t activeWarps = rowEnd > row0 ? min((uint32_t)NW, (rowEnd - row0 + RW - 1) / RW) : 0u;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NW); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, max(activeWarps, 1u)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (activeWarps == 0 || (warp < NW && warp >= activeWarps)) return;
 
     if (warp == NW) {
         // ------------------------------------------------------------ producer
@@ -469,8 +473,7 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
     static const int forceNT = getenv("CUSPMM_STAGED_NT") ? atoi(getenv("CUSPMM_STAGED_NT")) : 0;   // tuning hook
     // (31 warps x 2 rows on 256- or 128-column tiles, to give the CTAs of a 4096^2 matrix full row slots, measured slower than
     //  148 half-filled 512-column CTAs: 0.159 / 0.290 ms against 0.136 ms)
-    if (forceNT == 128) return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    if (forceNT == 256 && N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    if (forceNT == 128) return launch<Cfg<128, 31, 1, 64, 4>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     if (N % 512 == 0) {
         // Three shapes of the same kernel (measured in profiles/r01_staged_rw_tuning.txt):
         //   31 warps x 2 rows (1024 threads, 64 regs): 62-row panels, 8 warps per scheduler hide the
@@ -487,8 +490,14 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
         if (shape == 2) return launch<Cfg<512, 15, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         return launch<Cfg<512, 15, 4, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
-    if (N % 256 == 0) return launch<Cfg<256, 15, 8, 64, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    return launch<Cfg<128, 15, 8, 128, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    // N = 128, 256, 384: 128-column tiles, one row per warp (31 rows per CTA keep >= 1 wave of CTAs for M >= 4 500), 4 ring stages;
+    // chunks of 64 rows of B for sparse rows (fewer barrier rounds), 32 for dense ones (the 32-entry window lasts 2 chunks).
+    // 4000^2, N = 128 (ms): d = 0.5: 0.202 (sub-warp kernel 0.271, cuSPARSE 0.371); d = 0.1: 0.050 (0.072, 0.098).
+    // (Tried and dropped: rows on 8-lane groups, four rows per warp at a time -- 0.85 ms, too few warps per SM to hide the
+    //  shuffle -> LDS -> FMA chain; 15 warps x 8 rows -- 1.26 ms, 33 CTAs.)
+    const double density = (double)nnz / ((double)M * (double)K);
+    if (density >= 0.3) return launch<Cfg<128, 31, 1, 32, 4>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    return launch<Cfg<128, 31, 1, 64, 4>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
 }
 
 } // namespace staged
@@ -527,6 +536,9 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
     if (!vec_ok) return 4;
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
+    // N = 128: one 128-column tile, 31 rows per CTA (N = 256 / 384 would need row-wise TMA copies of 512 bytes: 25605^2,
+    // N = 256: 10.2 ms against 3.4 ms for the sub-warp kernel)
+    if (N == 128 && M >= 1024 && density * 31.0 >= 1.6) return 3;
     if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 1.6) {
         // staged.  The dual-path kernel (5) is faster when a CTA's panel re-uses every staged B row often enough for the
         // chunk to outlast the TMEM copy round trip: rows per CTA x density >= 5.5 non-zeros per B row (8 when the column

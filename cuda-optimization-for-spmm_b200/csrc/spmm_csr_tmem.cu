@@ -156,10 +156,12 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
     const uint32_t col0 = blockIdx.y * NT;
     const uint32_t row0 = blockIdx.x * rpc;
     const uint32_t rowEnd = min(M, row0 + rpc);
-    const uint32_t nchunks = (K + KC - 1) / KC;
+    // consumer warps without rows skip the pipeline (they would only spin on the barriers); with no rows at all nothing runs
+    const uint32_t activeWarps = rowEnd > row0 ? min((uint32_t)NW, (rowEnd - row0 + RW - 1) / RW) : 0u;
+    const uint32_t nchunks = activeWarps ? (K + KC - 1) / KC : 0u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(tma_full + s, 1); mbar_init(full + s, NI); mbar_init(empty + s, NW); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(tma_full + s, 1); mbar_init(full + s, NI); mbar_init(empty + s, max(activeWarps, 1u)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == NW) {
@@ -228,7 +230,7 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
             if (did) idle = 0;
             else { __nanosleep(64); if (++idle > (1u << 28)) __trap(); }   // ~20 s without progress: a lost arrive must fail loudly, not hang the GPU
         }
-    } else {
+    } else if (warp < activeWarps) {
         // ------------------------------------------------------------ consumers
         uint32_t wbase[RW], wj[RW], end[RW], bcol[RW], off[RW];
         float bval[RW];
