@@ -478,14 +478,16 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
         // Three shapes of the same kernel (measured in profiles/r01_staged_rw_tuning.txt):
         //   31 warps x 2 rows (1024 threads, 64 regs): 62-row panels, 8 warps per scheduler hide the
         //       shuffle -> LDS -> FMA latency; shared-memory pipe bound.  Best whenever a CTA gets >= 30 rows.
-        //   15 warps x 2 rows: 30-row panels for short matrices (M < 30 * SMs): every warp still has work.
+        //   31 warps x 1 row: 31-row panels for short matrices (M < 30 * SMs): twice the warps of 15 x 2 for the same rows
+        //       (4096^2: 0.139 -> 0.130 ms);  15 warps x 2 rows: the same on sliced ELL.
         //   15 warps x 4 rows: the first version (60-row panels); kept behind the tuning hook only.
         static const int forceRW = getenv("CUSPMM_STAGED_RW") ? atoi(getenv("CUSPMM_STAGED_RW")) : 0;   // tuning hook
         const uint32_t ytiles = N / 512;
         int shape = forceRW;
         // (sliced ELL keeps 15 x 4: its window refills are strided 128-byte-apart loads, and 16 warps sharing a
         //  slice through a 30 KB L1 measured 6 % slower than 8 warps: 5.24 vs 4.92 ms on large_25605)
-        if (shape == 0) shape = plan_grid(M, ytiles, 62).rpc >= 30 ? (SELL ? 4 : 31) : 2;
+        if (shape == 0) shape = plan_grid(M, ytiles, 62).rpc >= 30 ? (SELL ? 4 : 31) : (SELL ? 2 : 1);
+        if (shape == 1) return launch<Cfg<512, 31, 1, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         if (shape == 31) return launch<Cfg<512, 31, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         if (shape == 2) return launch<Cfg<512, 15, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         return launch<Cfg<512, 15, 4, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
