@@ -588,15 +588,14 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
     switch (variant) {
     case 1: {
         // column tile per warp: 512 columns (4 float4 per lane) re-read A least; few rows (or a forced tile) -> narrower tiles,
-        // so that a long row's entries are spread over several warps and more B rows are in flight per row
+        // so that a long row's entries are spread over several warps and more B rows are in flight per row (GL7d25: 0.082 /
+        // 0.061 / 0.053 ms at 512 / 256 / 128 columns; 16 B rows in flight per lane instead of 8: slower, short rows fall into the tail loop)
         static const int forceU = getenv("CUSPMM_ROWSPLIT_U") ? atoi(getenv("CUSPMM_ROWSPLIT_U")) : 0;   // tuning hook
         int U = N > 256 ? 4 : (N > 128 ? 2 : 1);
         if (forceU == 1 || forceU == 2 || forceU == 4) U = forceU;
         const dim3 grid(blocks, (N + 128u * U - 1) / (128u * U));
         if (U == 4) csr_rowsplit_vec_kernel<4, 2, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         else if (U == 2) csr_rowsplit_vec_kernel<2, 4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
-        else if (forceU == 1 && getenv("CUSPMM_ROWSPLIT_J16"))
-            csr_rowsplit_vec_kernel<1, 16, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         else csr_rowsplit_vec_kernel<1, 8, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);
         CUSPMM_LAUNCH_CHECK("csr_rowsplit_vec_kernel");
         return CUSPMM_OK;
