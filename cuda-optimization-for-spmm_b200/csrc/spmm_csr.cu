@@ -552,9 +552,10 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
         tmem_planned_grid(M, N, &ctas, &rpc);
         const double reuse = (double)rpc * density;
         // (on the sliced-ELL layout the staged kernel is slower to begin with, so the switch comes earlier: 4.5; with less than a
-        //  wave of CTAs the dual path still wins from ~15 non-zeros per B row: 4000^2 N=512 d=0.3 +5 %, d=0.5 +5..10 %)
+        //  wave of CTAs the dual path still wins from ~15 non-zeros per B row (8 on sliced ELL): 4000^2 N=512 d=0.3 +5 %,
+        //  d=0.5 +5..10 %)
         const double need = N == 512 ? (sell ? 4.5 : 5.5) : 8.0;
-        return ((ctas >= (uint64_t)sm_count() && reuse >= need) || reuse >= 15.0) ? 5 : 3;
+        return ((ctas >= (uint64_t)sm_count() && reuse >= need) || reuse >= (sell ? 8.0 : 15.0)) ? 5 : 3;
     }
     // very short rows: the nnz-balanced warp-per-row kernel wins once a row spans several 64-column tiles of the sub-warp
     // kernel (20000^2, 14 nnz/row, N=512: 0.047 vs 0.055 ms; 4000^2, 40 nnz/row, N=2048: 0.082 vs 0.087 ms)
