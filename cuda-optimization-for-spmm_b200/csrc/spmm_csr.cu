@@ -543,10 +543,9 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
     if (N == 128 && M >= 1024 && density * 31.0 >= 1.6) return 3;
     if (N % 512 == 0 && M >= 1024 && density * 60.0 >= 1.6) {
         // staged.  The dual-path kernel (5) is faster when a CTA's panel re-uses every staged B row often enough for the
-        // chunk to outlast the TMEM copy round trip: rows per CTA x density >= 5.5 non-zeros per B row (8 when the column
-        // tile is narrower than B, i.e. row-wise TMA copies), with at least one full wave of CTAs.  Measured (spmm_csr_tmem.cu,
-        // profiles/r01_sweep.jsonl): 25605^2 d=0.10 (5.8) +6 %, 20000^2 d=0.10 (4.6) -3 %, d=0.12 (5.5) +4 %, d=0.3..0.5 +28..32 %;
-        // N=4096: 11008x4096 d=0.10 (5.5) -20 %, d=0.15 (8.3) +1 %, d=0.5 +28 %
+        // chunk to outlast the TMEM copy round trip: rows per CTA x density >= 5.5 non-zeros per B row, with at least one full
+        // wave of CTAs.  Measured (spmm_csr_tmem.cu, profiles/r01_sweep.jsonl): 25605^2 d=0.10 (5.8) +6 %, 20000^2 d=0.10 (4.6) -3 %,
+        // d=0.12 (5.5) +4 %, d=0.3..0.5 +28..32 %; N=4096 (2-D tensor-map TMA): 11008x4096 d=0.10 (5.5) +6 %, d=0.5 +30 %
         uint64_t ctas = 0;
         uint32_t rpc = 0;
         tmem_planned_grid(M, N, &ctas, &rpc);
@@ -554,7 +553,7 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
         // (on the sliced-ELL layout the staged kernel is slower to begin with, so the switch comes earlier: 4.5; with less than a
         //  wave of CTAs the dual path still wins from ~15 non-zeros per B row (8 on sliced ELL): 4000^2 N=512 d=0.3 +5 %,
         //  d=0.5 +5..10 %)
-        const double need = N == 512 ? (sell ? 4.5 : 5.5) : 8.0;
+        const double need = sell ? 4.5 : 5.5;
         return ((ctas >= (uint64_t)sm_count() && reuse >= need) || reuse >= (sell ? 8.0 : 15.0)) ? 5 : 3;
     }
     // very short rows: the nnz-balanced warp-per-row kernel wins once a row spans several 64-column tiles of the sub-warp

@@ -21,7 +21,9 @@
 // trip.  The kernel below keeps variant 3's pipeline and uses TMEM for part of every chunk instead.
 #include "common.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no -lcuda)
 #include <stdlib.h>
+#include <string.h>
 
 namespace cuspmm_b200 {
 namespace tmemk {
@@ -63,6 +65,12 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// 2-D tiled TMA copy: box (c0 .. , c1 ..) of the tensor map -> shared memory, completion (full box bytes, rows past the end of
+// the tensor arrive as zeros) on the mbarrier
+__device__ __forceinline__ void tma_box_2d(void *dst, const CUtensorMap *map, uint32_t c0, uint32_t c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -141,7 +149,8 @@ template <class CFG, bool SELL>
 __global__ void __launch_bounds__(CFG::kThreads, 1)
 csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
                 const float *__restrict__ vals, uint32_t M, uint32_t K, uint32_t rpc,
-                const float *__restrict__ B, size_t ldb, float *__restrict__ C, size_t ldc) {
+                const float *__restrict__ B, size_t ldb, float *__restrict__ C, size_t ldc,
+                const __grid_constant__ CUtensorMap tmapB, int useTmap) {
     constexpr int NW = CFG::kNW, NI = CFG::kNI, TR = CFG::kTR, TS = CFG::kTS, RW = CFG::kRW, KC = CFG::kKC;
     constexpr int STAGES = CFG::kStages, NT = kNT;
     constexpr uint32_t kStageBytes = CFG::kStageBytes, kRowBytes = CFG::kRowBytes;
@@ -176,7 +185,7 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
     if (warp >= NW) {
         // ------------------------------------------------------------ issuers (issuer 0 = TMA producer too)
         const uint32_t j = warp - NW;
-        const bool rowwise = (size_t)NT != ldb && NI > 1;
+        const bool rowwise = (size_t)NT != ldb && NI > 1 && !useTmap;
         // Two task streams, both driven by non-blocking barrier tests so that neither holds up the other:
         //   TMA load of chunk c (issuer 0):  B rows -> ring stage c % 3, once chunk c - 3 is consumed
         //   copies of chunk c (all issuers): first TR rows of the stage -> TMEM stage c % TS, once the TMA data
@@ -189,6 +198,13 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
             const uint32_t k0 = c * KC;
             const uint32_t rows = min((uint32_t)KC, K - k0);
             unsigned char *dst = ring + (size_t)s * kStageBytes;
+            if (useTmap) {                            // column tile narrower than B: ONE 2-D tensor copy (32 rows x 2 KB box)
+                if (lane == 0) {
+                    mbar_expect_tx(tma_full + s, kStageBytes);
+                    tma_box_2d(dst, &tmapB, col0 / 2, k0, tma_full + s);      // the map counts 8-byte elements
+                }
+                return;
+            }
             if (lane == 0) mbar_expect_tx(tma_full + s, rows * kRowBytes);
             __syncwarp();
             if ((size_t)NT == ldb) {
@@ -395,6 +411,30 @@ csr_dual_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
     }
 }
 
+// B as a 2-D tensor of 8-byte elements (so that a 512-column box is 256 elements, the TMA box limit): dims (N/2, K), row
+// pitch ldb * 4 bytes, box (256, 32), no swizzle, rows past K read as zeros.  The driver's encoder is fetched once per process.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_tmap_B(CUtensorMap *map, const float *B, uint32_t K, uint32_t N, size_t ldb, uint32_t boxRows) {
+    static EncodeTiledFn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    if (!encode || (N & 1) || ((ldb * sizeof(float)) & 15) || (reinterpret_cast<uintptr_t>(B) & 15)) return false;
+    const cuuint64_t dims[2] = {N / 2, K};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldb * sizeof(float)};
+    const cuuint32_t box[2] = {256, boxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<float *>(B), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class CFG, bool SELL>
 static int launch_dual(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
                        const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
@@ -409,7 +449,11 @@ static int launch_dual(const uint32_t *rowPtrs, const uint32_t *colIdxs, const f
     const uint32_t ytiles = N / kNT;
     const GridPlan g = plan_grid(M, ytiles, CFG::kRows);
     dim3 grid(g.panels, ytiles);
-    kern<<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(rowPtrs, colIdxs, vals, M, K, g.rpc, B, ldb, C, ldc);
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    static const bool noTmap = getenv("CUSPMM_NO_TMAP") != nullptr;        // tuning hook: row-wise bulk copies instead
+    const int useTmap = ((size_t)kNT != ldb && !noTmap && make_tmap_B(&map, B, K, N, ldb, CFG::kKC)) ? 1 : 0;
+    kern<<<grid, CFG::kThreads, CFG::kSmemBytes, st>>>(rowPtrs, colIdxs, vals, M, K, g.rpc, B, ldb, C, ldc, map, useTmap);
     CUSPMM_LAUNCH_CHECK("csr_dual_kernel");
     return CUSPMM_OK;
 }
@@ -441,7 +485,10 @@ int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float
     //   its refill round trip                              16x2   4.51   5.89   7.10   9.68   15.11
     const double density = (double)nnz / ((double)M * (double)K);
     const bool sparse = shape == 1 || (shape != 2 && density < 0.2);
-    if ((size_t)tmemk::kNT != ldb) {      // row-wise TMA copies: a fourth issuer warp, issuer 0 only loads (28 consumers)
+    static const int wide4 = getenv("CUSPMM_TMEM_WIDE4") ? atoi(getenv("CUSPMM_TMEM_WIDE4")) : 1;   // tuning hook
+    // column tile narrower than B (2-D tensor-map TMA, or 32 row copies without it): 28 consumers + a fourth issuer warp
+    // (11008x4096 d=0.1: 2.32 ms against 2.35 with 29 + 3; without the tensor map 2.80)
+    if ((size_t)tmemk::kNT != ldb && wide4) {
         if (sparse) return tmemk::launch_dual<tmemk::DualCfg<28, 4, 10, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         return tmemk::launch_dual<tmemk::DualCfg<28, 4, 16, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
