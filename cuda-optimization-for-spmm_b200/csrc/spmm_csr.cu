@@ -553,7 +553,7 @@ int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool ve
         // (on the sliced-ELL layout the staged kernel is slower to begin with, so the switch comes earlier: 4.5; with less than a
         //  wave of CTAs the dual path still wins from ~15 non-zeros per B row (8 on sliced ELL): 4000^2 N=512 d=0.3 +5 %,
         //  d=0.5 +5..10 %)
-        const double need = sell ? 4.5 : 5.5;
+        const double need = sell ? 4.5 : 5.4;      // (5.5 measured; a shade lower so that "10 % x 55 rows" does not fall on the wrong side of rounding)
         return ((ctas >= (uint64_t)sm_count() && reuse >= need) || reuse >= (sell ? 8.0 : 15.0)) ? 5 : 3;
     }
     // very short rows: the nnz-balanced warp-per-row kernel wins once a row spans several 64-column tiles of the sub-warp
