@@ -131,7 +131,9 @@ static GridPlan plan_grid(uint32_t M, uint32_t ytiles, uint32_t rowSlots) {
 //   (1 - TR/32) * 16 wavefronts per non-zero + the TMA writes + the copy engine's reads of TR rows
 // instead of 16 per non-zero + the TMA writes.  TMEM: TS stages x TR rows x 16 columns <= 512 columns.
 // Warps: 0..NW-1 consumers, NW..NW+NI-1 copy issuers; issuer 0 also drives the TMA ring.
-// (Tried and dropped: keeping the TMEM rows out of the ring -- a separate double buffer for them and a 4..5-deep
+// (Tried and dropped: loading the TMEM rows of a chunk with their own bulk copy and barrier so that the copies into TMEM start before
+//  the rest of the chunk has landed -- the second barrier wait per chunk costs more than it saves: 4.19 vs 4.09 ms;
+//  keeping the TMEM rows out of the ring -- a separate double buffer for them and a 4..5-deep
 //  ring of the other rows -- measured 4.22 ms against 4.11 ms for this version on large_25605.)
 template <int NW, int NI, int TR, int TS, int KC = 32, int STAGES = 3>
 struct DualCfg {
