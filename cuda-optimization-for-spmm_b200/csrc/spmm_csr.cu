@@ -570,6 +570,8 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
                          uint32_t M, uint32_t K, uint32_t nnz, const float *B, uint32_t N, size_t ldb,
                          float *C, size_t ldc, int variant, cudaStream_t st) {
     CUSPMM_REQUIRE(variant >= 0 && variant <= CUSPMM_CSR_NUM_VARIANTS, "%s variant %d does not exist", SELL ? "ELL row" : "CSR", variant);
+    if (variant == 6)
+        return set_error(CUSPMM_ERR_WORKSPACE, "CSR variant 6 needs workspace: call cuspmm_spmm_csr_ws (cuspmm_spmm_csr_workspace bytes)");
     CUSPMM_REQUIRE(ldb >= N && ldc >= N, "ldb/ldc (%zu/%zu) must be >= N (%u)", ldb, ldc, N);
     if (M == 0 || N == 0) return CUSPMM_OK;
     CUSPMM_REQUIRE(rowPtrs && B && C && (nnz == 0 || (colIdxs && vals)), "null operand pointer");
@@ -620,8 +622,6 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
             return set_error(CUSPMM_ERR_UNSUPPORTED, "TMEM-staged kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
         return spmm_rows_tmem<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
     }
-    case 6:
-        return set_error(CUSPMM_ERR_WORKSPACE, "CSR variant 6 needs workspace: call cuspmm_spmm_csr_ws (cuspmm_spmm_csr_workspace bytes)");
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);
         csr_rowsplit_scalar_kernel<4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);

@@ -59,6 +59,23 @@ def test_argument_validation_needs_no_device(L):
     assert rc == 1                                               # ldb < N
 
 
+def test_csr_workspace_contract_needs_no_device(L):
+    """cuspmm_spmm_csr_workspace: 0 bytes for the row / staged kernels, a positive, nnz- and N-dependent size for the
+    row-cutting kernel (variant 6); variant 6 without workspace is refused before any CUDA call; the plain entry point
+    never runs it."""
+    L.cuspmm_spmm_csr_workspace.restype = ctypes.c_size_t
+    L.cuspmm_spmm_csr_workspace.argtypes = [ctypes.c_uint32] * 4 + [ctypes.c_int]
+    for v in (1, 2, 3, 4, 5):
+        assert L.cuspmm_spmm_csr_workspace(2798, 21074, 81671, 512, v) == 0
+    w6 = L.cuspmm_spmm_csr_workspace(2798, 21074, 81671, 512, 6)
+    assert w6 > 0 and w6 % 16 == 0
+    assert L.cuspmm_spmm_csr_workspace(2798, 21074, 81671, 128, 6) < w6          # fewer 128-column tiles
+    assert L.cuspmm_spmm_csr_workspace(2798, 21074, 81671, 512, 0) == w6         # few long rows: the selector may want it
+    assert L.cuspmm_spmm_csr_workspace(25605, 25605, 65571195, 512, 0) == 0      # staged territory: never
+    rc = L.cuspmm_spmm_csr(None, None, None, 4, 4, 0, None, 4, 4, None, 4, 6, None)
+    assert rc != 0 and b"workspace" in L.cuspmm_last_error()
+
+
 def test_plain_c_client_compiles_links_and_runs(tmp_path):
     """The header is C (not C++) and a gcc-built program links against the shared library."""
     import subprocess
