@@ -125,6 +125,45 @@ __device__ __forceinline__ void warp_lower_bound2(uint32_t n, uint64_t target0, 
     out0 = lo0;
     out1 = lo1;
 }
+// ----------------------------------------------------------------- mbarrier / TMA bulk-copy primitives
+// Shared by the staged CSR kernels (spmm_csr.cu), the dual-path kernel (spmm_csr_tmem.cu) and the tcgen05 BSR kernel
+// (spmm_bsr_tc.cu).  The wait loops differ per kernel (plain spin / suspend-time hint) and stay with them.
+namespace pipe {
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one try_wait on the phase with this parity (true: completed); hint_ns > 0: suspend-time hint for the hardware wait
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 0) {
+    uint32_t done;
+    if (hint_ns)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+// blocking wait; a lost arrive must fail loudly (trap), not hang the GPU
+template <uint32_t HINT_NS = 0, uint32_t MAX_SPINS = (1u << 27)>
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity, HINT_NS))
+        if (++spins > MAX_SPINS) __trap();
+}
+// 1-D TMA bulk copy global -> shared, completion (bytes) on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+} // namespace pipe
 #endif
+
 
 } // namespace cuspmm_b200

@@ -33,29 +33,11 @@ namespace bsrtc {
 constexpr int kThreads = 192;
 constexpr int kMaxTileN = 512;     // columns of C per CTA (4 UMMA M-tiles)
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done = 0, spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (done) break;
-        if (++spins > (1u << 27)) __trap();   // fail loudly instead of hanging the GPU
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
+using pipe::smem_u32;
+using pipe::mbar_init;
+using pipe::mbar_expect_tx;
+using pipe::bulk_g2s;
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { pipe::mbar_wait<0>(bar, parity); }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {   // arrives on bar when all prior MMAs are done
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -28,30 +28,14 @@
 namespace cuspmm_b200 {
 namespace tmemk {
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (woken by the arrive) or
-// the hint elapses, instead of spinning -- in the first version the poll loops were 27 % of all issued instructions
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done = 0, spins = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(2000u) : "memory");
-        if (done) break;
-        if (++spins > (1u << 24)) __trap();        // a lost arrive must fail loudly, not hang the GPU
-    }
-}
+using pipe::smem_u32;
+using pipe::mbar_init;
+using pipe::mbar_expect_tx;
+using pipe::mbar_arrive;
+using pipe::bulk_g2s;
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (woken by the arrive) or the
+// hint elapses, instead of spinning
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { pipe::mbar_wait<2000, (1u << 24)>(bar, parity); }
 // one non-blocking test of a phase (true: the phase with this parity has completed)
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -61,10 +45,6 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 // 2-D tiled TMA copy: box (c0 .. , c1 ..) of the tensor map -> shared memory, completion (full box bytes, rows past the end of
 // the tensor arrive as zeros) on the mbarrier
