@@ -12,6 +12,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcuspmm_b200.so")
+if os.environ.get("CUSPMM_LIB"):          # tuning hook: an alternative build of the same library
+    LIB_PATH = os.environ["CUSPMM_LIB"]
 _lib = None
 
 U32 = C.c_uint32

@@ -67,12 +67,20 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// ring depth: sized so that 3 CTAs fit on an SM for both block sizes (16.5 KB x 4 = 66 KB, 34 KB x 2 = 68 KB):
+// ring depth (measured, cfg4: 16x16 4 stages 0.275 ms, 6 stages 0.38 ms; 32x32 2 stages 0.192 ms, 3 stages 0.180 ms: the kernel
+// is bound by the bytes in flight from L2, ncu: 168 registers -> 2 CTAs per SM).  First sizing:
+// so that 3 CTAs fit on an SM for both block sizes (16.5 KB x 4 = 66 KB, 34 KB x 2 = 68 KB):
 // the prologue (TMEM alloc, barrier init) and the epilogue of one CTA then overlap the main loops of
 // the other two.  With 4 stages of 34 KB only one CTA fits and the 32x32 kernel was 2x slower.
+#ifndef CUSPMM_BSR16_STAGES
+#define CUSPMM_BSR16_STAGES 4
+#endif
+#ifndef CUSPMM_BSR32_STAGES
+#define CUSPMM_BSR32_STAGES 3
+#endif
 template <int BS>
 struct Smem {
-    static constexpr int kStages = BS == 16 ? 4 : 2;
+    static constexpr int kStages = BS == 16 ? CUSPMM_BSR16_STAGES : CUSPMM_BSR32_STAGES;
     static constexpr uint32_t kBlockBytes = BS * BS * 2;
     static constexpr uint32_t kSlabBytes = BS * kMaxTileN * 2;          // bs k-rows x 512 n x 16 bit
     static constexpr uint32_t kStageBytes = kSlabBytes + kBlockBytes;
