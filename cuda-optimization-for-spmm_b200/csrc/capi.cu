@@ -1,7 +1,10 @@
 // capi.cu -- error string, launch counter, device queries of the C ABI.
 #include "common.cuh"
 
+#include <map>
+#include <mutex>
 #include <stdarg.h>
+#include <utility>
 #include <string.h>
 
 namespace cuspmm_b200 {
@@ -19,23 +22,39 @@ int set_error(int status, const char *fmt, ...) {
 
 void count_launch(unsigned n) { g_launches += n; }
 
-struct DevProps { int sms = 0; size_t l2 = 0; bool ok = false; };
-static DevProps g_props[64];
+struct DevProps { int sms = 0; size_t l2 = 0; };
 
-static DevProps &props() {
+static DevProps props() {      // cached per device ordinal (any ordinal: a map, not a fixed table)
+    static std::mutex mu;
+    static std::map<int, DevProps> cache;
     int dev = 0;
     cudaGetDevice(&dev);
-    DevProps &p = g_props[dev & 63];
-    if (!p.ok) {
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) p.sms = v;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess) p.l2 = (size_t)v;
-        if (p.sms <= 0) p.sms = 148;
-        p.ok = true;
-    }
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    DevProps p;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) p.sms = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess) p.l2 = (size_t)v;
+    if (p.sms <= 0) p.sms = 148;
+    cache[dev] = p;
     return p;
 }
 int sm_count() { return props().sms; }
+
+int set_smem_once_impl(const void *kern, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = done.find({kern, dev});
+    if (it != done.end() && it->second >= bytes) return (int)cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) done[{kern, dev}] = bytes;
+    return (int)e;
+}
 size_t l2_bytes() { return props().l2; }
 
 } // namespace cuspmm_b200

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 
 #include "cuspmm_b200.h"
 
@@ -41,6 +42,14 @@ void count_launch(unsigned n = 1);
 
 int sm_count();          // SMs of the current device (cached per device)
 size_t l2_bytes();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): thread-safe, any device ordinal.  Keyed by the
+// kernel's ADDRESS: instantiations with the same signature share this function's type, so a per-type flag would be wrong.
+int set_smem_once_impl(const void *kern, size_t bytes);      // capi.cu; returns a cudaError_t
+template <typename Kern>
+static inline cudaError_t set_smem_once(Kern kern, size_t bytes) {
+    return (cudaError_t)set_smem_once_impl(reinterpret_cast<const void *>(kern), bytes);
+}
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -150,12 +159,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity, ui
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return done != 0;
 }
-// blocking wait; a lost arrive must fail loudly (trap), not hang the GPU
-template <uint32_t HINT_NS = 0, uint32_t MAX_SPINS = (1u << 27)>
+// blocking wait; a lost arrive must fail loudly (trap), not hang the GPU.  The bound is ELAPSED TIME (%globaltimer,
+// checked every 4096 polls), not a poll count: under a debugger, MPS time-slicing or a long preemption a healthy wait
+// may take arbitrarily many polls, but not 20 seconds of wall clock
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr uint64_t kWaitLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
+template <uint32_t HINT_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity, HINT_NS))
-        if (++spins > MAX_SPINS) __trap();
+    uint32_t polls = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity, HINT_NS)) {
+        if ((++polls & 4095u) == 0) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitLimitNs) __trap();
+        }
+    }
 }
 // 1-D TMA bulk copy global -> shared, completion (bytes) on the mbarrier
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {

@@ -268,6 +268,11 @@ struct cuspmmBsrTcPlan_s {
     int dev = 0;
 };
 
+static bool plan_on_current_device(const cuspmmBsrTcPlan_s *p) {
+    int dev = -1;
+    return cudaGetDevice(&dev) == cudaSuccess && dev == p->dev;
+}
+
 extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs,
                                          const float *blocks, uint32_t numBlockRows, uint32_t numBlocks, uint32_t bs,
                                          uint32_t K, uint32_t maxN, cuspmmBlockType type, void *stream) {
@@ -283,10 +288,11 @@ extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *b
     p->maxN = maxN; p->maxNpad = (maxN + 127) / 128 * 128;
     cudaGetDevice(&p->dev);
     const uint64_t total = (uint64_t)numBlocks * bs * bs;
-    if (cudaMalloc(&p->blocksQ, (total ? total : 1) * 2) != cudaSuccess ||
-        cudaMalloc(&p->Bq, (size_t)p->Kpad * p->maxNpad * 2) != cudaSuccess) {
+    cudaError_t me = cudaMalloc(&p->blocksQ, (total ? total : 1) * 2);
+    if (me == cudaSuccess) me = cudaMalloc(&p->Bq, (size_t)p->Kpad * p->maxNpad * 2);
+    if (me != cudaSuccess) {
         cudaFree(p->blocksQ); cudaFree(p->Bq); delete p;
-        return set_error(CUSPMM_ERR_CUDA, "cudaMalloc of the tensor-core BSR plan failed");
+        return set_error(CUSPMM_ERR_CUDA, "cudaMalloc of the tensor-core BSR plan failed: %s", cudaGetErrorString(me));
     }
     if (total) {
         const unsigned grid = (unsigned)((total + 255) / 256);
@@ -305,6 +311,7 @@ extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *b
 
 extern "C" int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan p, const float *B, uint32_t N, size_t ldb, void *stream) {
     CUSPMM_REQUIRE(p && B && N >= 1 && N <= p->maxN && ldb >= N, "bad arguments (N=%u, maxN=%u)", N, p ? p->maxN : 0);
+    CUSPMM_REQUIRE(plan_on_current_device(p), "the plan was created on device %d; make it current before prepare_B", p->dev);
     p->N = N;
     p->Npad = (N + 127) / 128 * 128;
     const uint64_t total = (uint64_t)(p->Kpad / 8) * p->Npad;
@@ -320,11 +327,7 @@ extern "C" int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan p, const float *B, uint32
 template <int BS, int FMT>
 static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
     auto kern = bsrtc::bsr_tc_kernel<BS, FMT>;
-    static bool attr_done[64] = {};
-    if (!attr_done[p->dev & 63]) {
-        CUSPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsrtc::Smem<BS>::kTotal));
-        attr_done[p->dev & 63] = true;
-    }
+    CUSPMM_CUDA(set_smem_once(kern, bsrtc::Smem<BS>::kTotal));
     dim3 grid(p->numBlockRows, (p->Npad + bsrtc::kMaxTileN - 1) / bsrtc::kMaxTileN);
     kern<<<grid, bsrtc::kThreads, bsrtc::Smem<BS>::kTotal, st>>>(p->blockRowPtrs, p->blockColIdxs, p->blocksQ, p->Bq, p->Npad, p->N, C, ldc);
     CUSPMM_LAUNCH_CHECK("bsr_tc_kernel");
@@ -334,6 +337,7 @@ static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
 extern "C" int cuspmm_bsr_tc_run(cuspmmBsrTcPlan p, float *C, size_t ldc, void *stream) {
     CUSPMM_REQUIRE(p && C && p->N >= 1, "prepare_B must be called before run");
     CUSPMM_REQUIRE(ldc >= p->N, "ldc must be >= N");
+    CUSPMM_REQUIRE(plan_on_current_device(p), "the plan was created on device %d; make it current before run", p->dev);
     if (p->numBlockRows == 0) return CUSPMM_OK;
     cudaStream_t st = as_stream(stream);
     if (p->bs == 16) return p->type == CUSPMM_BLK_BF16 ? launch_tc<16, 1>(p, C, ldc, st) : launch_tc<16, 0>(p, C, ldc, st);

@@ -423,13 +423,7 @@ template <class CFG, bool SELL>
 int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
            const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
     auto kern = csr_staged_kernel<CFG, SELL>;
-    static bool attr_done[64] = {};
-    int dev = 0;
-    CUSPMM_CUDA(cudaGetDevice(&dev));
-    if (!attr_done[dev & 63]) {
-        CUSPMM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CFG::kSmemBytes));
-        attr_done[dev & 63] = true;
-    }
+    CUSPMM_CUDA(set_smem_once(kern, CFG::kSmemBytes));
     const uint32_t ytiles = N / CFG::kNT;
     const GridPlan g = plan_grid(M, ytiles, CFG::kRows);
     dim3 grid(g.panels, ytiles);
@@ -480,6 +474,11 @@ template <bool SELL>
 int spmm_rows_tmem(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                    const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
 void tmem_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_per_cta);
+// variant 7: every B read from tensor memory, columns split over the TMEM lane quarters (spmm_csr_quad.cu)
+template <bool SELL>
+int spmm_rows_quad(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
+                   const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
+void quad_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_per_cta);
 // variant 6: nnz split that cuts rows, ordered carry fix-up (spmm_csr_split.cu); needs workspace
 size_t spmm_csr_split_workspace(uint32_t nnz, uint32_t N);
 int spmm_csr_split(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
@@ -592,6 +591,11 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
         if (!(vok && N % 512 == 0))
             return set_error(CUSPMM_ERR_UNSUPPORTED, "TMEM-staged kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
         return spmm_rows_tmem<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
+    }
+    case 7: {
+        if (!(vok && N % 512 == 0))
+            return set_error(CUSPMM_ERR_UNSUPPORTED, "all-TMEM kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
+        return spmm_rows_quad<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
     }
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);

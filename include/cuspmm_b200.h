@@ -66,8 +66,16 @@ int cuspmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
  *      (N % 512 == 0, else CUSPMM_ERR_UNSUPPORTED)
  *   6  nnz split that cuts rows between warps (merge-path style) with an ordered carry fix-up, for few / skewed rows;
  *      no atomics, fixed order; cut rows are rounded differently from 1..5 (partial sums first), uncut rows identically.
- *      Needs workspace: only through cuspmm_spmm_csr_ws. */
-#define CUSPMM_CSR_NUM_VARIANTS 6
+ *      Needs workspace: only through cuspmm_spmm_csr_ws.
+ *   7  every B read from tensor memory: TMA -> shared-memory ring -> tcgen05.cp.128x256b -> a 128-row TMEM ring of B; a warp
+ *      owns 8 rows x the 128 columns of its TMEM lane quarter and fetches B with tcgen05.ld.x4 (no shared-memory operand
+ *      reads at all); fp32 FMA in CSR order like 1..5 (N % 512 == 0, else CUSPMM_ERR_UNSUPPORTED)
+ *
+ * PRECONDITION for variants 0, 3, 5, 7 (and everything built on them: COO variant 2, sliced ELL, the host-buffer and multi-GPU
+ * entry points): column indices ascend strictly inside every row, as the reference's converter writes them
+ * (convert_mtx.py:127-143, scipy CSR with sorted indices).  Variants 1, 2, 4, 6 accept any order.  cuspmm_csr_check_sorted
+ * verifies it on the device. */
+#define CUSPMM_CSR_NUM_VARIANTS 7
 int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
                     uint32_t M, uint32_t K, uint32_t nnz,
                     const float *B_dev, uint32_t N, size_t ldb,
@@ -101,9 +109,10 @@ int cuspmm_spmm_coo(const uint32_t *rowIdxs_dev, const uint32_t *colIdxs_dev, co
  * s is W_s slots wide, slot-major: entry j of row s*32+i at slicePtrs[s] + j*32 + i;
  * padding colIdx 0xFFFFFFFF / value 0.  Replaces spmmELLWrapper1/2 / spmmELLK1/2
  * (include/engine/engine_ell.hpp:15-19, src/spmm/ell/spmm_ell_k{1,2}.cu). */
-#define CUSPMM_ELL_NUM_VARIANTS 4 /* 1 row kernels (warp / sub-warp per row); 2 staged (B tiles via TMA bulk
+#define CUSPMM_ELL_NUM_VARIANTS 5 /* 1 row kernels (warp / sub-warp per row); 2 staged (B tiles via TMA bulk
                                      copies); 3 slice per CTA with the slots staged through shared memory;
-                                     4 staged with the dual operand path (CSR variant 5 on the sliced layout) */
+                                     4 staged with the dual operand path (CSR variant 5 on the sliced layout);
+                                     5 every B read from tensor memory (CSR variant 7 on the sliced layout) */
 int cuspmm_spmm_sell(const uint32_t *slicePtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
                      uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots /* = slicePtrs[numSlices] */,
                      const float *B_dev, uint32_t N, size_t ldb,
