@@ -2,20 +2,31 @@
 """bench.py -- SpMM GFLOP/s (2*nnz*N) + HBM GB/s (% roofline) vs cuSPARSE, BASELINE.json's metric.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload NAME] [--format csr|coo|ell] [--variant V] [--gather]
+                    [--workload NAME] [--format csr|coo|ell|bsr16|bsr32] [--variant V] [--no-extras]
 
-A "step" is one C = A*B over the workload.  Default workload: large_25605 (25605^2, 90 % sparse,
-N = 512, CSR) -- the configuration BASELINE.json's target is quoted on; it fits one GPU.
-N > 1 (launched by torchrun, one rank per GPU): weak scaling -- every rank owns one row panel of
-25605 rows of a (N*25605) x 25605 matrix (its own seed), B is replicated, no data-path collective
-(rows of C are independent: src/spmm/csr/spmm_csr.cpp:15-27); --gather adds an NCCL all_gather of C.
+A "step" is one C = A*B over the workload.  Default workload: large_25605 (25605^2, 90 % sparse, N = 512, CSR) -- the
+configuration BASELINE.json's target is quoted on; it fits one GPU.
 
-Timing: CUDA events on the launching stream around each step, W warm-up steps first, barrier +
-synchronize on both sides, max over ranks.  A + B + C = 630 MB > the 126 MB L2, so no flush is
-needed between steps ("inputs_larger_than_l2"); workloads under 252 MB get a 256 MB read between steps.  `e2e` is the same multiply through the
-host-buffer C-ABI entry point (cuspmm_spmm_csr_host: pinned host operands, H2D + kernels + D2H
-inside the timed region).  `cpu_baseline` times the reference's own spmmCSRCpu (oracle/_ref) on a
-bounded row sample on this box's host cores.  Prints ONE JSON line on rank 0.
+N > 1 (torchrun, one rank per GPU): STRONG scaling of that ONE matrix.  Every rank generates the same matrix from the same
+seed, the row panels come from the device partitioner (cuspmm_partition_rows_by_nnz: nnz-balanced contiguous rows), a rank
+keeps only its own panel of A and its rows of C; B is replicated.  No collective in the device-timed data path (rows of C are
+independent: src/spmm/csr/spmm_csr.cpp:15-27).  `value` = the whole matrix's flops / the slowest rank's device time.
+
+`e2e` = the same multiply from HOST buffers, copies inside the timed region, wall clock, max over ranks:
+    N = 1: cuspmm_spmm_csr_host (pinned CSR + B in, C out, pipelined row panels);
+    N > 1: every rank uploads ITS panel of A over its own PCIe link and ITS 1/N row slice of B, B is completed by an NCCL
+           all-gather over NVLink, cuspmm_spmm_csr_host_devB multiplies (kernels wait for the all-gather) and returns the
+           rank's rows of C to the host.
+Every N also checks sampled rows of every rank's panel against the CPU oracle (`parity`).
+
+Timing: CUDA events on the launching stream around each step, W >= 3 warm-up steps, barrier + synchronize on both sides, max over
+ranks.  A + B + C = 630 MB > the 126 MB L2, so no flush is needed at N = 1 ("inputs_larger_than_l2"); whenever a rank's
+operands are under 252 MB a 256 MB buffer is read between steps, outside the per-step events.
+
+N = 1 only: `cpu_baseline` (the reference's own spmmCSRCpu from oracle/_ref on all host threads, one row block per thread, plus the
+single-thread figure the reference would show), same-run cuSPARSE, and -- unless --no-extras -- the sub-records `formats` (COO, ELL,
+BSR 16/32 on the headline shape), `configs` (the other BASELINE configs) and `convert` (device converters in GB/s).
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -33,17 +44,20 @@ sys.path.insert(0, ROOT)
 
 METRIC = "spmm_gflops"
 UNIT = "GFLOP/s"
+L2_BYTES = 126e6
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    out = {"hbm": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "bf16": 1682.6, "bf16_src": "fallback"}
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            out["hbm"], out["hbm_src"] = float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            out["bf16"], out["bf16_src"] = float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return out
 
 
 class ClockSampler:
@@ -108,30 +122,326 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def sample_rows_for_seconds(run_rows, target_s, start_rows=16, max_rows=None):
-    """Calibrate a row-sample size so that run_rows(rows) takes about target_s seconds."""
-    rows = start_rows
-    t0 = time.perf_counter(); run_rows(rows); dt = time.perf_counter() - t0
-    est = max(rows, int(rows * target_s / max(dt, 1e-6)))
-    if max_rows:
-        est = min(est, max_rows)
-    return max(est, 1)
-
-
-def cpu_reference_csr(orc, a_host, B_host, rows):
-    """The reference's own spmmCSRCpu when oracle/_ref exists (kind 'reference', 1 thread: the
-    reference is single-threaded, src/spmm/csr/spmm_csr.cpp:15-27), else the oracle port on all
-    host threads (kind 'port')."""
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_spmm_rows(orc, a_host, B_host, rows, threads):
+    """The reference's own spmmCSRCpu (oracle/_ref; src/spmm/csr/spmm_csr.cpp:15-27 is single-threaded) on rows [0, rows)
+    of a_host.  threads > 1: the rows are cut into `threads` nnz-balanced blocks and the SAME reference function runs on each
+    block in its own host thread (ctypes releases the GIL), i.e. the reference's code on all host cores.  Without oracle/_ref
+    the oracle port (OpenMP over rows) stands in.  -> (seconds, kind, threads used, nnz processed)."""
     import numpy as np
-    sub = orc.CSR(rows, a_host.K, a_host.rowPtrs[:rows + 1], a_host.colIdxs[:int(a_host.rowPtrs[rows])],
-                  a_host.vals[:int(a_host.rowPtrs[rows])])
-    if orc.ref_lib() is not None:
-        t0 = time.perf_counter(); orc.spmm_csr(sub, B_host, use_ref=True); dt = time.perf_counter() - t0
-        return dt, "reference", 1, sub.nnz
-    t0 = time.perf_counter(); orc.spmm_csr(sub, B_host, omp=True); dt = time.perf_counter() - t0
-    return dt, "port", orc.lib().oracle_num_threads(), sub.nnz
+    rp = a_host.rowPtrs
+    nnz = int(rp[rows])
+    if orc.ref_lib() is None:
+        sub = orc.CSR(rows, a_host.K, rp[:rows + 1], a_host.colIdxs[:nnz], a_host.vals[:nnz])
+        t0 = time.perf_counter(); orc.spmm_csr(sub, B_host, omp=threads > 1); dt = time.perf_counter() - t0
+        return dt, "port", (orc.lib().oracle_num_threads() if threads > 1 else 1), nnz
+    threads = max(1, min(threads, rows))
+    cuts = [int(np.searchsorted(rp[:rows + 1], (g * nnz) // threads, side="left")) for g in range(threads)] + [rows]
+    cuts = sorted(set(cuts))
+    blocks = []
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        i0, i1 = int(rp[r0]), int(rp[r1])
+        blocks.append(orc.CSR(r1 - r0, a_host.K, (rp[r0:r1 + 1] - rp[r0]).astype(np.uint32), a_host.colIdxs[i0:i1], a_host.vals[i0:i1]))
+    if len(blocks) == 1:
+        t0 = time.perf_counter(); orc.spmm_csr(blocks[0], B_host, use_ref=True); dt = time.perf_counter() - t0
+        return dt, "reference", 1, nnz
+    ths = [threading.Thread(target=orc.spmm_csr, args=(blk, B_host), kwargs={"use_ref": True}) for blk in blocks]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.perf_counter() - t0, "reference", len(blocks), nnz
 
 
+def calibrated_rows(run, target_s, start_rows, max_rows):
+    """Rows such that run(rows) takes about target_s seconds (one probe run)."""
+    dt = run(start_rows)[0]
+    est = int(start_rows * target_s / max(dt, 1e-6))
+    return max(start_rows, min(est, max_rows))
+
+
+def numpy_csr_rows(np, K, density, rows, seed):
+    rng = np.random.default_rng(seed)
+    lens = rng.binomial(K, density, size=rows)
+    rp = np.zeros(rows + 1, np.uint32); rp[1:] = np.cumsum(lens)
+    ci = np.concatenate([np.sort(rng.choice(K, size=int(n), replace=False)) for n in lens]).astype(np.uint32)
+    va = rng.uniform(-1, 1, size=int(rp[-1])).astype(np.float32)
+    return rp, ci, va
+
+
+def reference_arm(args, orc, np):
+    """--impl reference: the reference's own CPU SpMM (oracle/_ref, else the oracle port) with all the host threads, each step a
+    bounded row sample of the same workload.  Inputs are generated with numpy (same distribution, same density; no GPU)."""
+    from importlib import util
+    spec = util.spec_from_file_location("wl_named", os.path.join(ROOT, "cuda-optimization-for-spmm_b200", "workloads.py"))
+    text = open(spec.origin).read()       # only the NAMED table is needed; avoid importing torch.cuda
+    ns = {}
+    exec(text[text.index("NAMED = {"):text.index("def gen_csr_device")], ns)
+    M, K, density, N = ns["NAMED"][args.workload]
+    threads = os.cpu_count() or 1
+    rows_cap = min(M, 64 * threads)
+    rp, ci, va = numpy_csr_rows(np, K, density, rows_cap, 618)
+    B = np.random.default_rng(619).uniform(-1, 1, size=(K, N)).astype(np.float32)
+    a = orc.CSR(rows_cap, K, rp, ci, va)
+    run = lambda r: cpu_spmm_rows(orc, a, B, r, threads)
+    total_steps = max(1, args.steps + args.warmup)
+    per_step_s = max(0.5, min(5.0, 120.0 / total_steps))
+    rows_s = calibrated_rows(run, per_step_s, min(rows_cap, 2 * threads), rows_cap)
+    for _ in range(args.warmup):
+        run(rows_s)
+    t = 0.0
+    kind, cores, snnz = "port", 1, 0
+    for _ in range(args.steps):
+        dt, kind, cores, snnz = run(rows_s)
+        t += dt
+    ms = t / args.steps * 1e3
+    val = 2.0 * snnz * N / (ms * 1e-3) / 1e9
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {M}x{K} A, density {density}, B {K}x{N}, CSR; each step = rows "
+                                  f"[0,{rows_s}) ({snnz} nnz) through the reference's spmmCSRCpu on {cores} host threads"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "kind": kind, "cores": cores,
+                            "sample": f"{rows_s} rows ({snnz} nnz) per step, one nnz-balanced row block per thread",
+                            "host_cpus": os.cpu_count()},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ GPU helpers
+class Ctx:
+    pass
+
+
+def timed_steps(torch, step, steps, warmup, flush=None):
+    """-> per-step milliseconds (CUDA events on the current stream; L2 evicted before each step when `flush` is given)."""
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        if flush is not None:
+            flush.sum()
+        e0.record(); step(); e1.record()
+    torch.cuda.synchronize()
+    return [e0.elapsed_time(e1) for e0, e1 in evs]
+
+
+def sampled_parity(cx, rp, ci, va, M, K, Bd, Cd, nrows=8, rounded=None):
+    """max component-wise relative error |C - Cref| / (|A||B|) of `nrows` sampled rows of a device CSR product against the
+    CPU oracle (oracle/spmm_oracle.c restating spmmCSRCpu)."""
+    np, orc, wl = cx.np, cx.orc, cx.wl
+    if M == 0:
+        return 0.0
+    rows = sorted(set(int(x) for x in np.linspace(0, M - 1, num=min(nrows, M))))
+    B_host = Bd.cpu().numpy()
+    worst = 0.0
+    for r in rows:
+        srp, sci, sva = wl.csr_sample_to_host(rp, ci, va, r, r + 1)
+        a = orc.CSR(1, K, srp, sci, sva)
+        ref = orc.spmm_csr(a, B_host)
+        den = orc.absprod_csr(a, B_host)
+        got = Cd[r:r + 1].cpu().numpy()
+        worst = max(worst, float(orc.max_rel_err(got, ref, den)))
+    return worst
+
+
+def roofline_record(pk, alg_bytes, ms, flops, nnz, N, sm_mhz=None, traffic=None):
+    achieved = alg_bytes / (ms * 1e-3) / 1e9
+    clk = sm_mhz or 1965.0
+    t_hbm = alg_bytes / (pk["hbm"] * 1e9) * 1e3
+    t_fp32 = flops / (148 * 128 * 2 * clk * 1e6) * 1e3
+    t_l1 = (4.0 * nnz * N) / (148 * 128 * clk * 1e6) * 1e3
+    return {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+            "traffic": traffic, "peak_source": pk["hbm_src"], "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms,
+            "bounds_ms": {"hbm": t_hbm, "fp32_fma": t_fp32, "smem_operand_bw": t_l1},
+            "binding": max((("hbm", t_hbm), ("fp32_fma", t_fp32), ("smem_operand_bw", t_l1)), key=lambda x: x[1])[0]}
+
+
+def lookup_traffic(workload, fmt, kernel):
+    """DRAM bytes of one launch from the committed ncu --set full capture -- only when that capture was taken on the SAME
+    kernel the selector launches now (the file records the kernel per entry); otherwise null rather than a stale number."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tj.get(f"{workload}/{fmt}")
+        if ent and ent.get("kernel") == kernel:
+            return ent["bytes"]
+    except Exception:
+        pass
+    return None
+
+
+def bsr_case(cx, M, K, density, N, bs, seed, steps, dtype="bf16"):
+    """BASELINE configs[3]: block-sparse A (density = fraction of bs x bs blocks stored), bf16 blocks on tcgen05."""
+    torch, b, wl, pk = cx.torch, cx.b, cx.wl, cx.pk
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    nbr, nbc = (M + bs - 1) // bs, (K + bs - 1) // bs
+    mask = torch.rand((nbr, nbc), generator=g, device="cuda") < density
+    brp = torch.zeros(nbr + 1, dtype=torch.int64, device="cuda"); brp[1:] = torch.cumsum(mask.sum(dim=1, dtype=torch.int64), 0)
+    bci = mask.nonzero(as_tuple=False)[:, 1].to(torch.int32)
+    nb = int(bci.numel())
+    blocks = torch.rand(nb * bs * bs, generator=g, device="cuda") * 2 - 1
+    brp = brp.to(torch.int32)
+    Mp, Kp = nbr * bs, nbc * bs
+    Bd = wl.gen_dense_device(Kp, N, seed=619)
+    Cd = torch.empty((Mp, N), dtype=torch.float32, device="cuda")
+    nnz = nb * bs * bs
+    flops = 2.0 * nnz * N
+    t0 = time.perf_counter()
+    plan = b.BsrTcPlan(brp, bci, blocks, nbr, bs, Kp, N, dtype=dtype)
+    torch.cuda.synchronize()
+    plan_ms = (time.perf_counter() - t0) * 1e3
+    prep = timed_steps(torch, lambda: plan.prepare_B(Bd), 3, 1)
+    alg_bytes = 2 * nnz + 4 * nb + 4 * (nbr + 1) + 2 * Kp * N + 4 * Mp * N
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda") if alg_bytes < 2 * L2_BYTES else None
+    ts = timed_steps(torch, lambda: plan.run(out=Cd), steps, 3, flush)
+    ms = statistics.median(ts)
+    tf = flops / (ms * 1e-3) / 1e12
+    rec = {"format": f"bsr{bs}", "kernel": "bsr_tc (tcgen05)", "dtype": f"{dtype} blocks and B, f32 accumulate", "M": Mp, "K": Kp, "N": N,
+           "blocks": nb, "block_density": density, "ms": ms, "ms_min": min(ts), "gflops_executed": flops / (ms * 1e-3) / 1e9,
+           "prepare_B_ms": statistics.median(prep), "plan_create_ms_wall": plan_ms,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": tf / pk["bf16"],
+                        "peak_source": pk["bf16_src"], "algorithmic_bytes_per_launch": alg_bytes,
+                        "hbm_GBs": alg_bytes / (ms * 1e-3) / 1e9, "hbm_frac": alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm"]}}
+    # parity: sampled block rows against the oracle on the ROUNDED operands (the stated tensor-core tolerance, 2e-5)
+    try:
+        np, orc = cx.np, cx.orc
+        rnd = orc.bf16_round if dtype == "bf16" else orc.fp16_round
+        Bh = rnd(Bd.cpu().numpy())
+        worst = 0.0
+        for R in sorted(set(int(x) for x in np.linspace(0, nbr - 1, num=4))):
+            i0, i1 = int(brp[R].item()), int(brp[R + 1].item())
+            sub = orc.BSR(bs, Kp, bs, bs, np.array([0, i1 - i0], np.uint32), bci[i0:i1].cpu().numpy().view(np.uint32).copy(),
+                          rnd(blocks[i0 * bs * bs:i1 * bs * bs].cpu().numpy()))
+            ref = orc.spmm_bsr(sub, Bh)
+            den = orc.absprod_csr(orc.csr_from_dense(np.abs(orc.to_dense(sub))), np.abs(Bh))
+            worst = max(worst, float(orc.max_rel_err(Cd[R * bs:(R + 1) * bs].cpu().numpy(), ref, den)))
+        rec["parity"] = {"max_rel_err_vs_oracle_on_rounded_operands": worst, "tolerance": 2e-5, "ok": worst <= 2e-5,
+                         "sample": "4 block rows"}
+    except Exception as ex:
+        rec["parity"] = {"error": str(ex)[:160]}
+    try:
+        tmp = torch.empty_like(Cd)
+        avg, mn = b.cusparse_spmm_bsr(brp, bci, blocks, nbr, nbc, bs, Bd, tmp, warmup=1, iters=3)
+        rec["cusparse"] = {"alg": "BSR fp32 ALG_DEFAULT", "ms_avg": avg, "speedup_vs_cusparse": avg / ms}
+        del tmp
+    except Exception as ex:
+        rec["cusparse"] = {"error": str(ex)[:160]}
+    # end to end from host buffers: upload fp32 blocks + B, cast / re-tile on the device, multiply, download C
+    try:
+        h = [t.cpu().pin_memory() for t in (brp, bci, blocks, Bd)]
+        C_h = torch.empty((Mp, N), dtype=torch.float32).pin_memory()
+        variant = 2 if dtype == "bf16" else 3
+        b.spmm_bsr_host(h[0], h[1], h[2], nbr, bs, bs, Kp, h[3], C_h, variant=variant)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            b.spmm_bsr_host(h[0], h[1], h[2], nbr, bs, bs, Kp, h[3], C_h, variant=variant)
+        ems = (time.perf_counter() - t0) * 1e3 / 2
+        rec["e2e"] = {"ms_per_step": ems, "value": flops / (ems * 1e-3) / 1e9, "unit": UNIT, "api": "cuspmm_spmm_bsr_host",
+                      "h2d_bytes_per_step": 4 * (nbr + 1) + 4 * nb + 4 * nnz + 4 * Kp * N, "d2h_bytes_per_step": 4 * Mp * N,
+                      "same_result": bool((C_h.cuda() == Cd).all().item())}
+    except Exception as ex:
+        rec["e2e"] = {"error": str(ex)[:200]}
+    plan.close()
+    return rec
+
+
+def sparse_case(cx, name, M, K, density, N, fmts, steps, seed=618, pre=None):
+    """One BASELINE shape, formats `fmts` of (csr, coo, ell): ms (median), GFLOP/s, kernel picked, x cuSPARSE, roofline with the
+    in-run algorithmic bytes, sampled-row parity vs the oracle."""
+    torch, b, wl, pk = cx.torch, cx.b, cx.wl, cx.pk
+    rp, ci, va = pre if pre is not None else wl.gen_csr_device(M, K, density, seed=seed)
+    Bd = wl.gen_dense_device(K, N, seed=619)
+    Cd = torch.empty((M, N), dtype=torch.float32, device="cuda")
+    nnz = int(ci.numel())
+    flops = 2.0 * nnz * N
+    out = {}
+    small = wl.csr_bytes(M, K, N, nnz) < 2 * L2_BYTES
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda") if small else None
+    cus = {}
+    for fmt in fmts:
+        rows = None
+        if fmt == "csr":
+            alg = wl.csr_bytes(M, K, N, nnz)
+            step = lambda: b.spmm_csr(rp, ci, va, M, K, Bd, variant=0, out=Cd)
+            kern = b.CSR_KERNEL_NAMES.get(b.csr_selected_variant(M, K, nnz, N))
+        elif fmt == "coo":
+            rows = torch.repeat_interleave(torch.arange(M, device="cuda", dtype=torch.int32), (rp[1:] - rp[:-1]).to(torch.int64))
+            alg = wl.coo_bytes(M, K, N, nnz)
+            step = lambda: b.spmm_coo(rows, ci, va, M, K, Bd, variant=0, out=Cd)
+            kern = "coo->" + str(b.CSR_KERNEL_NAMES.get(b.csr_selected_variant(M, K, nnz, N)))
+        else:
+            sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
+            alg = wl.sell_bytes(M, K, N, int(sc.numel()), int(sp.numel()) - 1)
+            step = lambda: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=0, out=Cd)
+            kern = "sell->" + str(b.CSR_KERNEL_NAMES.get(b.csr_selected_variant(M, K, int(sc.numel()), N, sell=True)))
+        ts = timed_steps(torch, step, steps, 3, flush)
+        ms = statistics.median(ts)
+        rec = {"ms": ms, "ms_min": min(ts), "gflops": flops / (ms * 1e-3) / 1e9, "kernel": kern, "nnz": nnz,
+               "roofline": roofline_record(pk, alg, ms, flops, nnz, N),
+               "l2": "l2_flushed_between_steps" if small else "inputs_larger_than_l2"}
+        err = sampled_parity(cx, rp, ci, va, M, K, Bd, Cd)
+        rec["parity"] = {"max_rel_err_vs_oracle": err, "tolerance": 1e-5, "ok": err <= 1e-5, "sample": "8 rows"}
+        which = 1 if fmt == "coo" else 0
+        if which not in cus:
+            try:
+                tmp = torch.empty_like(Cd)
+                rws = rows if which == 1 else rp
+                if flush is None:
+                    avg, mn = b.cusparse_spmm(which, rws, ci, va, M, K, Bd, tmp, warmup=1, iters=3)
+                else:
+                    b.cusparse_spmm(which, rws, ci, va, M, K, Bd, tmp, warmup=1, iters=1)
+                    tt = []
+                    for _ in range(5):
+                        flush.sum()
+                        tt.append(b.cusparse_spmm(which, rws, ci, va, M, K, Bd, tmp, warmup=0, iters=1)[0])
+                    avg, mn = statistics.median(tt), min(tt)
+                cus[which] = avg
+                del tmp
+            except Exception as ex:
+                cus[which] = None
+                rec["cusparse_error"] = str(ex)[:160]
+        if cus.get(which):
+            rec["cusparse"] = {"alg": "COO_ALG4" if which else "CSR_ALG2", "ms": cus[which], "speedup_vs_cusparse": cus[which] / ms}
+            if fmt == "ell":
+                rec["cusparse"]["note"] = "cuSPARSE has no sliced-ELL SpMM: compared with its CSR_ALG2 on the same matrix"
+        out[fmt] = rec
+    return out
+
+
+def convert_bench(cx, rp, ci, va, M, K):
+    """The device converters as the HBM-bound kernels they are: GB/s of compulsory bytes against the measured HBM peak."""
+    torch, b, pk = cx.torch, cx.b, cx.pk
+    nnz = int(ci.numel())
+    out = {}
+
+    def rec(name, fn, bytes_):
+        try:
+            ts = timed_steps(torch, fn, 3, 1)
+            ms = statistics.median(ts)
+            out[name] = {"ms": ms, "algorithmic_bytes": bytes_, "GBs": bytes_ / (ms * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": bytes_ / (ms * 1e-3) / 1e9 / pk["hbm"]}
+        except Exception as ex:
+            out[name] = {"error": str(ex)[:160]}
+    sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
+    slots = int(sc.numel())
+    rec("csr_to_sell32", lambda: b.csr_to_sell(rp, ci, va, M), 4 * (M + 1) * 2 + 8 * nnz + 8 * slots)
+    del sp, sc, sv
+    rows = torch.repeat_interleave(torch.arange(M, device="cuda", dtype=torch.int32), (rp[1:] - rp[:-1]).to(torch.int64))
+    rec("coo_to_csr_rowptrs", lambda: b.coo_to_csr_rowptrs(rows, M), 4 * (M + 1))
+    rec("partition_rows_by_nnz_x8", lambda: b.partition_rows_by_nnz(rp, M, nnz, 8), 4 * (M + 1))
+    rec("csr_check_sorted", lambda: b.csr_check_sorted(rp, ci, M, K), 4 * (M + 1) + 4 * nnz)
+    del rows
+    out["note"] = ("bytes = compulsory reads + writes of the conversion; coo_to_csr_rowptrs and the partitioner search instead of "
+                   "streaming (M+1 binary / 32-ary searches), so their GB/s is not a bandwidth figure; CSR->BSR is measured on the "
+                   "block-sparse configs by scripts/convert_bench.py (unstructured 10 % fills every 16x16 block: 2.6 GB of fp32 blocks)")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -141,10 +451,10 @@ def main():
     ap.add_argument("--workload", default="large_25605")
     ap.add_argument("--format", default="csr", choices=["csr", "coo", "ell", "bsr16", "bsr32"])
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--gather", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=8.0)
     ap.add_argument("--no-cusparse", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the formats / configs / convert sub-records (N = 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -153,7 +463,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     import numpy as np
-    from oracle import oracle as orc   # CPU-baseline leg only
+    from oracle import oracle as orc   # CPU-baseline / parity-check legs only
 
     if args.impl == "reference":
         if rank != 0:
@@ -167,78 +477,87 @@ def main():
     b = pkg.binding
     import importlib
     wl = importlib.import_module("cuspmm_b200.workloads")
+    sh = importlib.import_module("cuspmm_b200.sharding")
 
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU: there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = b.lib()
-
-    M, K, density, N = wl.NAMED[args.workload]
-    if not args.format.startswith("bsr"):
-        rp, ci, va = wl.gen_csr_device(M, K, density, seed=618 + rank)
-        Bd = wl.gen_dense_device(K, N, seed=619)          # the same B on every rank (replicated operand)
-        nnz = int(ci.numel())
-        Cd = torch.empty((M, N), dtype=torch.float32, device="cuda")
-        flops = 2.0 * nnz * N
-
-    fmt = args.format
-    tensor = None
-    if fmt.startswith("bsr"):
-        # BASELINE configs[3]: the same M x K with 10 % of the bs x bs blocks stored, bf16 blocks on tcgen05
-        # tensor cores (fp32 accumulate in TMEM); "nnz" = stored block elements (executed flops)
-        bs = int(fmt[3:])
-        g = torch.Generator(device="cuda"); g.manual_seed(618 + rank)
-        nbr, nbc = (M + bs - 1) // bs, (K + bs - 1) // bs
-        mask = torch.rand((nbr, nbc), generator=g, device="cuda") < density
-        brp = torch.zeros(nbr + 1, dtype=torch.int64, device="cuda"); brp[1:] = torch.cumsum(mask.sum(dim=1, dtype=torch.int64), 0)
-        bci = mask.nonzero(as_tuple=False)[:, 1].to(torch.int32)
-        nb = int(bci.numel())
-        blocks = torch.rand(nb * bs * bs, generator=g, device="cuda") * 2 - 1
-        brp = brp.to(torch.int32)
-        Bd = wl.gen_dense_device(nbc * bs, N, seed=619)
-        M, K = nbr * bs, nbc * bs
-        Cd = torch.empty((M, N), dtype=torch.float32, device="cuda")
-        nnz = nb * bs * bs
-        flops = 2.0 * nnz * N
-        plan = b.BsrTcPlan(brp, bci, blocks, nbr, bs, K, N, dtype="bf16")
-        plan.prepare_B(Bd)
-        alg_bytes = 2 * nnz + 4 * nb + 4 * (nbr + 1) + 2 * K * N + 4 * M * N
-        step = lambda: plan.run(out=Cd)
-        tensor = True
-    elif fmt == "csr":
-        alg_bytes = wl.csr_bytes(M, K, N, nnz)
-        step = lambda: b.spmm_csr(rp, ci, va, M, K, Bd, variant=args.variant, out=Cd)
-    elif fmt == "coo":
-        rows = torch.repeat_interleave(torch.arange(M, device="cuda", dtype=torch.int32), (rp[1:] - rp[:-1]).to(torch.int64))
-        alg_bytes = wl.coo_bytes(M, K, N, nnz)
-        step = lambda: b.spmm_coo(rows, ci, va, M, K, Bd, variant=args.variant, out=Cd)
-    else:
-        sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
-        alg_bytes = wl.sell_bytes(M, K, N, int(sc.numel()), int(sp.numel()) - 1)
-        step = lambda: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=args.variant, out=Cd)
+    cx = Ctx()
+    cx.torch, cx.b, cx.wl, cx.np, cx.orc, cx.pk = torch, b, wl, np, orc, measured_peaks()
+    pk = cx.pk
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    M, K, density, N = wl.NAMED[args.workload]
+    fmt = args.format
+
+    if fmt.startswith("bsr"):        # stand-alone tensor-core BSR line (one GPU; the default line carries it under "formats")
+        assert world == 1, "--format bsr16/bsr32 is a single-GPU line"
+        sampler = ClockSampler(local); sampler.start(); sampler.mark_start()
+        rec = bsr_case(cx, M, K, density, N, int(fmt[3:]), 618, args.steps)
+        sampler.mark_end()
+        out = {"metric": METRIC, "value": rec["gflops_executed"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": 3,
+               "ms_per_step": rec["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": rec["dtype"],
+               "data": "synthetic", "config": {"workload": f"{args.workload} block-sparse {fmt}", "format": fmt},
+               "gpu_launches": args.steps, "roofline": rec["roofline"], "e2e": rec.get("e2e"), "cusparse": rec.get("cusparse"),
+               "parity": rec.get("parity"), "prepare_B_ms": rec["prepare_B_ms"], "clocks": sampler.stop()}
+        print(json.dumps(out), flush=True)
+        return 0
+
+    # ---- the ONE matrix (same seed on every rank) and this rank's panel of it
+    rp, ci, va = wl.gen_csr_device(M, K, density, seed=618)
+    nnz_total = int(ci.numel())
+    Bd = wl.gen_dense_device(K, N, seed=619)          # replicated operand
+    if world > 1:
+        splits = b.partition_rows_by_nnz(rp, M, nnz_total, world)       # device partitioner, identical on every rank
+        r0, r1 = int(splits[rank]), int(splits[rank + 1])
+        i0, i1 = int(rp[r0].item()), int(rp[r1].item())
+        rp_l = (rp[r0:r1 + 1] - rp[r0]).contiguous()
+        ci_l, va_l = ci[i0:i1].clone(), va[i0:i1].clone()
+        del rp, ci, va
+        torch.cuda.empty_cache()
+    else:
+        splits = np.array([0, M], dtype=np.uint32)
+        r0, r1, rp_l, ci_l, va_l = 0, M, rp, ci, va
+    Ml = r1 - r0
+    nnz = int(ci_l.numel())
+    Cd = torch.empty((Ml, N), dtype=torch.float32, device="cuda")
+    flops_l = 2.0 * nnz * N
+    flops_total = 2.0 * nnz_total * N
+
+    if fmt == "csr":
+        alg_l = wl.csr_bytes(Ml, K, N, nnz)
+        alg_total = wl.csr_bytes(M, K, N, nnz_total)
+        step = lambda: b.spmm_csr(rp_l, ci_l, va_l, Ml, K, Bd, variant=args.variant, out=Cd)
+        kvar = args.variant or b.csr_selected_variant(Ml, K, nnz, N)
+        kernel_name = b.CSR_KERNEL_NAMES.get(kvar)
+    elif fmt == "coo":
+        rows_l = torch.repeat_interleave(torch.arange(Ml, device="cuda", dtype=torch.int32), (rp_l[1:] - rp_l[:-1]).to(torch.int64))
+        alg_l, alg_total = wl.coo_bytes(Ml, K, N, nnz), wl.coo_bytes(M, K, N, nnz_total)
+        step = lambda: b.spmm_coo(rows_l, ci_l, va_l, Ml, K, Bd, variant=args.variant, out=Cd)
+        kernel_name = "coo variant %d" % args.variant
+    else:
+        sp, sc, sv = b.csr_to_sell(rp_l, ci_l, va_l, Ml)
+        alg_l = wl.sell_bytes(Ml, K, N, int(sc.numel()), int(sp.numel()) - 1)
+        alg_total = alg_l if world == 1 else None
+        step = lambda: b.spmm_sell(sp, sc, sv, Ml, K, Bd, variant=args.variant, out=Cd)
+        kernel_name = "sell variant %d" % args.variant
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
         step()
-    if args.gather and world > 1:
-        gathered = [torch.empty_like(Cd) for _ in range(world)]
-        dist.all_gather(gathered, Cd)
     barrier()
 
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    # timing rule: inputs larger than L2, or L2 evicted between timed steps.  The default workload is 630 MB; smaller
-    # ones (--workload medium_*) get a 256 MB read between steps, outside the per-step events
-    l2_flush = None
-    if alg_bytes < 2 * 126e6:
-        l2_flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")
+    # timing rule: inputs larger than L2, or L2 evicted between timed steps (outside the per-step events)
+    l2_flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda") if alg_l < 2 * L2_BYTES else None
     L.cuspmm_reset_launch_count()
     barrier()
     sampler.mark_start()
@@ -248,199 +567,206 @@ def main():
             l2_flush.sum()
         e0.record()
         step()
-        if args.gather and world > 1:
-            dist.all_gather(gathered, Cd)
         e1.record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
     sampler.mark_end()
-    launches = int(L.cuspmm_launch_count())
+    launches = int(sh.reduce_sum(float(L.cuspmm_launch_count()), device="cuda"))
     clocks = sampler.stop() if rank == 0 else None
     per_step = [e0.elapsed_time(e1) for e0, e1 in evs]
-    sh = importlib.import_module("cuspmm_b200.sharding")
-    # whole-job throughput: all ranks' flops / the slowest rank's device time
-    value, ms_per_step = sh.job_throughput(sum(per_step), args.steps, flops, device="cuda")
-    flops_all = sh.reduce_sum(flops, device="cuda")
+    # whole-job throughput: the whole matrix's flops / the slowest rank's device time
+    ms_local = sum(per_step) / args.steps
+    ms_per_step = sh.reduce_max(ms_local, device="cuda")
+    value = flops_total / (ms_per_step * 1e-3) / 1e9
+    rank_ms = [0.0] * world
+    rank_nnz = [0] * world
+    if world > 1:
+        tt = torch.zeros(world, dtype=torch.float64, device="cuda"); tt[rank] = ms_local
+        nn = torch.zeros(world, dtype=torch.float64, device="cuda"); nn[rank] = nnz
+        dist.all_reduce(tt); dist.all_reduce(nn)
+        rank_ms, rank_nnz = [float(x) for x in tt.tolist()], [int(x) for x in nn.tolist()]
+    else:
+        rank_ms, rank_nnz = [ms_local], [nnz]
 
-    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    # ---- parity: sampled rows of THIS rank's panel against the CPU oracle, every N (worst over ranks)
+    parity = None
+    try:
+        err = sampled_parity(cx, rp_l, ci_l, va_l, Ml, K, Bd, Cd) if fmt == "csr" else \
+            sampled_parity(cx, rp_l, ci_l, va_l, Ml, K, Bd, Cd)
+        worst = sh.reduce_max(err, device="cuda")
+        # a checksum over all panels: sum(C) in fp64 against (1^T A) B, both reduced over the ranks
+        colsum = torch.zeros(K, dtype=torch.float64, device="cuda")
+        colsum.index_add_(0, ci_l.to(torch.int64), va_l.to(torch.float64))
+        want = float(sh.reduce_sum(float((colsum @ Bd.to(torch.float64)).sum().item()), device="cuda"))
+        got = float(sh.reduce_sum(float(Cd.to(torch.float64).sum().item()), device="cuda"))
+        scale = float(sh.reduce_sum(float((colsum.abs() @ Bd.abs().to(torch.float64)).sum().item()), device="cuda"))
+        parity = {"max_rel_err_vs_oracle": worst, "tolerance": 1e-5, "sample": "8 rows of every rank's panel",
+                  "checksum_rel_diff": abs(got - want) / max(scale, 1e-30), "ok": bool(worst <= 1e-5 and abs(got - want) <= 1e-6 * scale)}
+    except Exception as ex:
+        parity = {"error": str(ex)[:200], "ok": False}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region, wall clock, max over ranks
     e2e = None
     try:
-        if tensor:
-            raise RuntimeError("the host-buffer entry point exists for CSR; BSR e2e not measured")
-        rp_h, ci_h, va_h = rp.cpu().pin_memory(), ci.cpu().pin_memory(), va.cpu().pin_memory()
-        B_h = Bd.cpu().pin_memory()
-        C_h = torch.empty((M, N), dtype=torch.float32).pin_memory()
-        b.spmm_csr_host(rp_h, ci_h, va_h, M, K, B_h, C_h, variant=args.variant)      # warm-up (allocations)
+        if fmt != "csr":
+            raise RuntimeError("the default e2e leg is CSR; COO / ELL / BSR host entries are timed in the 'formats' sub-records")
+        rp_h, ci_h, va_h = rp_l.cpu().pin_memory(), ci_l.cpu().pin_memory(), va_l.cpu().pin_memory()
+        C_h = torch.empty((Ml, N), dtype=torch.float32).pin_memory()
+        if world == 1:
+            B_h = Bd.cpu().pin_memory()
+            e2e_step = lambda: b.spmm_csr_host(rp_h, ci_h, va_h, Ml, K, B_h, C_h, variant=args.variant)
+            api = "cuspmm_spmm_csr_host (pinned host CSR + B in, C out; wall clock around the call)"
+            h2d = 4 * (M + 1) + 8 * nnz_total + 4 * K * N
+        else:
+            ks = (K + world - 1) // world                    # B rows per rank (padded so that the slices are equal)
+            B_full = torch.zeros((ks * world, N), dtype=torch.float32, device="cuda")
+            B_slice = torch.empty((ks, N), dtype=torch.float32, device="cuda")
+            Bs_h = torch.zeros((ks, N), dtype=torch.float32).pin_memory()
+            k0, k1 = rank * ks, min(K, (rank + 1) * ks)
+            if k1 > k0:
+                Bs_h[:k1 - k0] = Bd[k0:k1].cpu()
+
+            def e2e_step():
+                B_slice.copy_(Bs_h, non_blocking=True)                      # this rank's slice of B over its own PCIe link
+                dist.all_gather_into_tensor(B_full, B_slice)                # completed over NVLink
+                return b.spmm_csr_host_devB(rp_h, ci_h, va_h, Ml, K, B_full[:K], C_h, variant=args.variant)
+            api = ("per rank: H2D of its A panel + its 1/N slice of B, NCCL all_gather of B over NVLink, "
+                   "cuspmm_spmm_csr_host_devB, D2H of its C rows; wall clock, max over ranks")
+            h2d = 4 * (M + world) + 8 * nnz_total + 4 * ks * world * N
+        e2e_step()                                                            # warm-up (allocations, NCCL channels)
         barrier()
         t0 = time.perf_counter()
         dev_ms = 0.0
         for _ in range(args.e2e_steps):
-            dev_ms += b.spmm_csr_host(rp_h, ci_h, va_h, M, K, B_h, C_h, variant=args.variant)
+            dev_ms += e2e_step()
         barrier()
-        e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.e2e_steps], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        h2d = 4 * (M + 1) + 8 * nnz + 4 * K * N
-        d2h = 4 * M * N
-        e2e = {"value": flops_all / (float(e2e_ms.item()) * 1e-3) / 1e9, "unit": UNIT,
-               "ms_per_step": float(e2e_ms.item()), "device_ms_per_step": dev_ms / args.e2e_steps,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "api": "cuspmm_spmm_csr_host (pinned host CSR + B in, C out; wall clock around the call)",
-               "same_result": bool((C_h.cuda() == Cd).all().item()) if fmt == "csr" else None}
+        e2e_ms = sh.reduce_max((time.perf_counter() - t0) * 1e3 / args.e2e_steps, device="cuda")
+        same = bool((C_h.cuda() == Cd).all().item())
+        same = bool(sh.reduce_max(0.0 if same else 1.0, device="cuda") == 0.0)
+        e2e = {"value": flops_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms,
+               "device_ms_per_step_rank0": dev_ms / args.e2e_steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * M * N,
+               "api": api, "same_result_as_device_path": same}
     except Exception as ex:      # report, never hide
-        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:200]}
+        e2e = {"value": None, "unit": UNIT, "error": str(ex)[:300]}
+
+    # ---- same-run cuSPARSE on this rank's panel (max over ranks)
+    cusparse = None
+    if not args.no_cusparse and fmt in ("csr", "coo"):
+        try:
+            tmp = torch.empty_like(Cd)
+            which, rws = (0, rp_l) if fmt == "csr" else (1, rows_l)
+            if l2_flush is None:
+                avg, mn = b.cusparse_spmm(which, rws, ci_l, va_l, Ml, K, Bd, tmp, warmup=2, iters=5)
+            else:     # same protocol as ours: L2 evicted before every timed launch
+                b.cusparse_spmm(which, rws, ci_l, va_l, Ml, K, Bd, tmp, warmup=2, iters=1)
+                ts = []
+                for _ in range(7):
+                    l2_flush.sum()
+                    ts.append(b.cusparse_spmm(which, rws, ci_l, va_l, Ml, K, Bd, tmp, warmup=0, iters=1)[0])
+                avg, mn = statistics.median(ts), min(ts)
+            avg = sh.reduce_max(avg, device="cuda")
+            cusparse = {"alg": "CSR_ALG2" if fmt == "csr" else "COO_ALG4", "ms_avg": avg, "ms_min_rank0": mn,
+                        "gflops": flops_total / (avg * 1e-3) / 1e9, "speedup_vs_cusparse": avg / ms_per_step,
+                        "max_abs_diff_vs_ours_rank0": float((tmp - Cd).abs().max().item()),
+                        "note": "the same row panels through cusparseSpMM on every rank, max over ranks"}
+            del tmp
+        except Exception as ex:
+            cusparse = {"error": str(ex)[:200]}
 
     out = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        # the bounds of SURVEY.md section 8d / BASELINE.md section 3
-        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-        t_hbm = alg_bytes / (peak * 1e9) * 1e3
-        t_fp32 = flops / (148 * 128 * 2 * sm_clock * 1e6) * 1e3
-        t_l1 = (4.0 * nnz * N) / (148 * 128 * sm_clock * 1e6) * 1e3
-        traffic = None
-        try:     # measured once per kernel change with ncu --set full (never under the timed run)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if fmt == "csr":      # variant 0 = the selector: dual-path kernel (5) on both workloads below
-                key = {("large_25605", 0): "large_25605/csr/dual", ("large_25605", 5): "large_25605/csr/dual",
-                       ("large_25605", 3): "large_25605/csr/staged", ("large_25605_s50", 0): "large_25605_s50/csr/dual",
-                       ("large_25605_s50", 5): "large_25605_s50/csr/dual"}.get((args.workload, args.variant))
-                if key:
-                    traffic = tj[key]["bytes"]
-        except Exception:
-            pass
+        sm_clock = (clocks or {}).get("sm_mhz")
+        roof = roofline_record(pk, alg_l, ms_per_step, flops_l, nnz, N, sm_clock,
+                               lookup_traffic(args.workload, fmt, kernel_name) if world == 1 else None)
+        roof["frac_of_binding_bound"] = max(roof["bounds_ms"].values()) / ms_per_step
+        roof["kernel"] = kernel_name
+        roof["note"] = ("per launch of rank 0's kernel (algorithmic bytes of ITS panel / its device time; peak = one GPU). fp32 CUDA-core "
+                        "SpMM at this density is bound by SM-local operand bandwidth (one distinct B element per FMA), not HBM: "
+                        "smem_operand_bw = all B reads through LDS at 128 B/clk/SM; see DESIGN.md")
+        imb = max(rank_nnz) * world / max(sum(rank_nnz), 1)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {M}x{K} A, density {density} (nnz {nnz} on rank 0), "
-                                   f"B {K}x{N}, {fmt.upper()} variant {args.variant} (0 = selector)",
-                       "format": fmt, "M_per_gpu": M, "K": K, "N": N, "nnz_per_gpu": nnz,
-                       "parallelism": f"row panels x{world}, B replicated" + (", NCCL all_gather of C" if args.gather else ", C left sharded"),
-                       "l2": ("inputs_larger_than_l2 (A+B+C = %.0f MB vs 126 MB L2; no flush)" % (alg_bytes / 1e6)) if l2_flush is None
-                             else ("l2_flushed_between_steps (A+B+C = %.0f MB; 256 MB read before every timed step, outside the events)" % (alg_bytes / 1e6)),
+            "config": {"workload": f"{args.workload}: ONE {M}x{K} A, density {density} (nnz {nnz_total}), B {K}x{N}, "
+                                   f"{fmt.upper()} variant {args.variant} (0 = selector -> {kernel_name})",
+                       "format": fmt, "M": M, "K": K, "N": N, "nnz": nnz_total,
+                       "parallelism": (f"{world} nnz-balanced contiguous row panels (cuspmm_partition_rows_by_nnz), one per GPU; "
+                                       "B replicated; C left sharded by rows; no data-path collective") if world > 1 else "single GPU",
+                       "row_splits": [int(x) for x in splits], "nnz_per_rank": rank_nnz, "nnz_imbalance": imb,
+                       "ms_per_rank": rank_ms,
+                       "l2": ("inputs_larger_than_l2 (A+B+C per rank = %.0f MB vs 126 MB L2; no flush)" % (alg_l / 1e6)) if l2_flush is None
+                             else ("l2_flushed_between_steps (A+B+C per rank = %.0f MB; 256 MB read before every timed step, outside the events)" % (alg_l / 1e6)),
                        "seed": 618},
             "gpu_launches": launches,
             "wall_ms_timed_region": wall_ms,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": ms_per_step,
-                         "bounds_ms": {"hbm": t_hbm, "fp32_fma": t_fp32, "smem_operand_bw": t_l1},
-                         "binding": max((("hbm", t_hbm), ("fp32_fma", t_fp32), ("smem_operand_bw", t_l1)), key=lambda x: x[1])[0],
-                         "frac_of_binding_bound": max(t_hbm, t_fp32, t_l1) / ms_per_step,
-                         "note": "fp32 CUDA-core SpMM at this density is bound by SM-local operand bandwidth (one "
-                                 "distinct B element per FMA), not HBM; smem_operand_bw = all B reads through LDS at 128 B/clk/SM, "
-                                 "which the dual-path kernel (CSR 5) undercuts by serving part of them from tensor memory: see DESIGN.md"},
+            "roofline": roof,
             "e2e": e2e,
+            "parity": parity,
+            "cusparse": cusparse,
             "clocks": clocks,
         }
-        if tensor:
-            tpeak = 1682.6
+    # ---- N = 1 only: CPU baseline and the other formats / configs (rank 0 alone exists)
+    if world == 1 and rank == 0:
+        try:
+            threads = os.cpu_count() or 1
+            rows_cap = min(M, 64 * threads)
+            srp, sci, sva = wl.csr_sample_to_host(rp_l, ci_l, va_l, 0, rows_cap)
+            a_host = orc.CSR(rows_cap, K, srp, sci, sva)
+            B_host = Bd.cpu().numpy()
+            run_all = lambda r: cpu_spmm_rows(orc, a_host, B_host, r, threads)
+            rows_s = calibrated_rows(run_all, args.cpu_seconds, min(rows_cap, 2 * threads), rows_cap)
+            dt, kind, cores, snnz = run_all(rows_s)
+            out["cpu_baseline"] = {"value": 2.0 * snnz * N / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+                                   "sample": f"rows [0,{rows_s}) of the workload ({snnz} nnz, {dt:.1f} s): the reference's spmmCSRCpu "
+                                             f"(oracle/_ref, built -O2) on one nnz-balanced row block per host thread",
+                                   "host_cpus": os.cpu_count()}
+            run_one = lambda r: cpu_spmm_rows(orc, a_host, B_host, r, 1)
+            rows_1 = calibrated_rows(run_one, args.cpu_seconds / 2, 8, rows_cap)
+            dt, kind, cores, snnz = run_one(rows_1)
+            out["cpu_baseline_single_thread"] = {"value": 2.0 * snnz * N / dt / 1e9, "unit": UNIT, "cores": 1, "kind": kind,
+                                                 "sample": f"rows [0,{rows_1}) ({snnz} nnz, {dt:.1f} s): as the reference runs it (one thread)"}
+        except Exception as ex:
+            out["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+        if not args.no_extras and args.workload == "large_25605" and fmt == "csr":
+            t_ex = time.perf_counter()
             try:
-                tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
-            except Exception:
-                pass
-            tf = flops / (ms_per_step * 1e-3) / 1e12
-            out["dtype"] = "bf16 blocks and B, f32 accumulate"
-            out["roofline"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                               "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)",
-                               "algorithmic_bytes_per_launch": alg_bytes, "hbm_GBs": achieved, "hbm_frac": achieved / peak,
-                               "binding": "l2_to_sm_operand_gather",
-                               "note": "at 10 % block density every stored block needs its own bs x N slab of B from L2 "
-                                       "(nb*bs*N*2 bytes): the kernel is bound by L2->SM bandwidth (ncu: lts 68 %), not the tensor pipe"}
-            try:
-                tmp = torch.empty_like(Cd)
-                avg, mn = b.cusparse_spmm_bsr(brp, bci, blocks, nbr, nbc, bs, Bd, tmp, warmup=1, iters=3)
-                out["cusparse"] = {"alg": "BSR fp32 ALG_DEFAULT", "ms_avg": avg, "speedup_vs_cusparse": avg / ms_per_step}
+                out["convert"] = convert_bench(cx, rp_l, ci_l, va_l, M, K)
             except Exception as ex:
-                out["cusparse"] = {"error": str(ex)[:200]}
-        # ---- same-run cuSPARSE baseline
-        if not args.no_cusparse and fmt in ("csr", "coo"):
-            try:
-                tmp = torch.empty_like(Cd)
-                which, rws = (0, rp) if fmt == "csr" else (1, rows)
-                if l2_flush is None:
-                    avg, mn = b.cusparse_spmm(which, rws, ci, va, M, K, Bd, tmp, warmup=2, iters=5)
-                else:     # same protocol as ours: L2 evicted before every timed launch
-                    b.cusparse_spmm(which, rws, ci, va, M, K, Bd, tmp, warmup=2, iters=1)
-                    ts = []
-                    for _ in range(7):
-                        l2_flush.sum()
-                        ts.append(b.cusparse_spmm(which, rws, ci, va, M, K, Bd, tmp, warmup=0, iters=1)[0])
-                    avg, mn = statistics.median(ts), min(ts)
-                out["cusparse"] = {"alg": "CSR_ALG2" if fmt == "csr" else "COO_ALG4", "ms_avg": avg, "ms_min": mn,
-                                   "gflops": flops / (avg * 1e-3) / 1e9, "speedup_vs_cusparse": avg / ms_per_step,
-                                   "max_abs_diff_vs_ours": float((tmp - Cd).abs().max().item())}
-                del tmp
+                out["convert"] = {"error": str(ex)[:200]}
+            formats = {}
+            try:      # the headline shape in the other formats (same matrix), then the tensor-core BSR rows of configs[3]
+                formats.update(sparse_case(cx, args.workload, M, K, density, N, ("coo", "ell"), 5, pre=(rp_l, ci_l, va_l)))
             except Exception as ex:
-                out["cusparse"] = {"error": str(ex)[:200]}
-        # ---- CPU baseline: bounded row sample of the same workload, this box's host cores
-        if world == 1 and not tensor:
-            try:
-                rows_cap = min(M, 4096)
-                srp, sci, sva = wl.csr_sample_to_host(rp, ci, va, 0, rows_cap)
-                a_host = orc.CSR(rows_cap, K, srp, sci, sva)
-                B_host = Bd.cpu().numpy()
-                run = lambda r: cpu_reference_csr(orc, a_host, B_host, r)
-                rows_s = sample_rows_for_seconds(run, args.cpu_seconds, 8, rows_cap)
-                dt, kind, cores, snnz = run(rows_s)
-                out["cpu_baseline"] = {"value": 2.0 * snnz * N / dt / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-                                       "sample": f"rows [0,{rows_s}) of the workload ({snnz} nnz, {dt:.1f} s); "
-                                                 f"oracle/_ref = the reference's spmmCSRCpu built -O2",
-                                       "host_cpus": os.cpu_count()}
-            except Exception as ex:
-                out["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
+                formats["error_coo_ell"] = str(ex)[:200]
+            del rp_l, ci_l, va_l
+            torch.cuda.empty_cache()
+            for bs in (16, 32):
+                try:
+                    formats[f"bsr{bs}"] = bsr_case(cx, M, K, density, N, bs, 618, 10)
+                except Exception as ex:
+                    formats[f"bsr{bs}"] = {"error": str(ex)[:200]}
+            out["formats"] = formats
+            configs = {}
+            plan = [("medium_4096", ("csr", "coo", "ell"), None), ("medium_4000_s99", ("csr", "ell"), 2048),
+                    ("medium_4000_s90", ("csr", "ell"), 128), ("medium_4000_s50", ("csr", "ell"), 2048),
+                    ("large_20000", ("csr",), None), ("large_25605_s50", ("csr",), None),
+                    ("ffn_11008x4096_s90", ("csr",), None), ("ffn_11008x4096_s50", ("csr",), None)]
+            for name, fmts, n_over in plan:
+                try:
+                    m_, k_, d_, n_ = wl.NAMED[name]
+                    n_ = n_over or n_
+                    configs[f"{name}_N{n_}"] = sparse_case(cx, name, m_, k_, d_, n_, fmts, 5)
+                    torch.cuda.empty_cache()
+                except Exception as ex:
+                    configs[name] = {"error": str(ex)[:200]}
+            out["configs"] = configs
+            out["extras_wall_s"] = time.perf_counter() - t_ex
+    if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
-
-
-def reference_arm(args, orc, np):
-    """--impl reference: the reference's own CPU SpMM (oracle/_ref, else the oracle port) on a bounded
-    row sample of the same workload per step.  Inputs are generated with numpy (same distribution,
-    same density; no GPU is touched)."""
-    from importlib import util
-    spec = util.spec_from_file_location("wl_named", os.path.join(ROOT, "cuda-optimization-for-spmm_b200", "workloads.py"))
-    # only the NAMED table is needed; avoid importing torch.cuda
-    text = open(spec.origin).read()
-    ns = {}
-    exec(text[text.index("NAMED = {"):text.index("def gen_csr_device")], ns)
-    M, K, density, N = ns["NAMED"][args.workload]
-    rng = np.random.default_rng(618)
-    rows_cap = 256
-    lens = rng.binomial(K, density, size=rows_cap)
-    rp = np.zeros(rows_cap + 1, np.uint32); rp[1:] = np.cumsum(lens)
-    ci = np.concatenate([np.sort(rng.choice(K, size=int(n), replace=False)) for n in lens]).astype(np.uint32)
-    va = rng.uniform(-1, 1, size=int(rp[-1])).astype(np.float32)
-    B = rng.uniform(-1, 1, size=(K, N)).astype(np.float32)
-    a = orc.CSR(rows_cap, K, rp, ci, va)
-    run = lambda r: cpu_reference_csr(orc, a, B, r)
-    total_steps = max(1, args.steps + args.warmup)
-    per_step_s = max(0.5, min(5.0, 150.0 / total_steps))
-    rows_s = sample_rows_for_seconds(run, per_step_s, 4, rows_cap)
-    for _ in range(args.warmup):
-        run(rows_s)
-    t = 0.0
-    kind, cores, snnz = "port", 1, 0
-    for _ in range(args.steps):
-        dt, kind, cores, snnz = run(rows_s)
-        t += dt
-    ms = t / args.steps * 1e3
-    val = 2.0 * snnz * N / (ms * 1e-3) / 1e9
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {M}x{K} A, density {density}, B {K}x{N}, CSR; each step = rows "
-                                  f"[0,{rows_s}) ({snnz} nnz) through the reference's spmmCSRCpu"},
-           "cpu_baseline": {"value": val, "unit": UNIT, "kind": kind, "cores": cores,
-                            "sample": f"{rows_s} rows ({snnz} nnz) per step", "host_cpus": os.cpu_count()},
-           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
     return 0
 
 

@@ -38,6 +38,7 @@ def lib():
         L.cuspmm_spmm_coo_workspace.restype = SZ
         L.cuspmm_spmm_coo_workspace.argtypes = [U32, U32, U32, C.c_int]
         L.cuspmm_spmm_csr.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P]
+        L.cuspmm_csr_selected_variant.argtypes = [U32, U32, U32, U32, C.c_int]
         L.cuspmm_spmm_csr_workspace.restype = SZ
         L.cuspmm_spmm_csr_workspace.argtypes = [U32, U32, U32, U32, C.c_int]
         L.cuspmm_spmm_csr_ws.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P, SZ, P]
@@ -52,6 +53,12 @@ def lib():
         L.cuspmm_partition_rows_by_nnz.argtypes = [P, U32, U32, U32, C.POINTER(U32), P]
         L.cuspmm_coo_to_csr_rowptrs.argtypes = [P, U32, U32, P, P]
         L.cuspmm_spmm_csr_host.argtypes = [P, P, P, U32, U32, U32, P, U32, P, C.c_int, C.POINTER(C.c_float)]
+        L.cuspmm_spmm_csr_host_devB.argtypes = [P, P, P, U32, U32, U32, P, SZ, P, U32, P, C.c_int, C.POINTER(C.c_float)]
+        L.cuspmm_spmm_coo_host.argtypes = [P, P, P, U32, U32, U32, P, U32, P, C.c_int, C.POINTER(C.c_float)]
+        L.cuspmm_spmm_sell_host.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, P, C.c_int, C.POINTER(C.c_float)]
+        L.cuspmm_spmm_bsr_host.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, P, C.c_int, C.POINTER(C.c_float)]
+        L.cuspmm_host_pipeline_release.argtypes = [C.c_int]
+        L.cuspmm_csr_check_sorted.argtypes = [P, P, U32, U32, C.POINTER(U32), P]
         L.cuspmm_host_alloc.argtypes = [C.POINTER(P), SZ]
         L.cuspmm_host_free.argtypes = [P]
         L.cuspmm_cusparse_spmm.argtypes = [C.c_int, P, P, P, U32, U32, U32, P, U32, P, C.c_int, C.c_int, C.c_int,
@@ -59,6 +66,10 @@ def lib():
         L.cuspmm_cusparse_spmm_bsr.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, P, C.c_int, C.c_int,
                                                C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.cuspmm_mgpu_create_csr.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32]
+        L.cuspmm_mgpu_create_coo.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32]
+        L.cuspmm_mgpu_create_sell.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32, U32]
+        L.cuspmm_mgpu_create_bsr.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32, U32]
+        L.cuspmm_mgpu_get_counts.argtypes = [P, C.POINTER(U32)]
         L.cuspmm_mgpu_set_B.argtypes = [P, P, U32]
         L.cuspmm_mgpu_run.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
         L.cuspmm_mgpu_get_splits.argtypes = [P, C.POINTER(U32)]
@@ -135,6 +146,15 @@ def spmm_csr(rowPtrs, colIdxs, vals, M, K, B, variant=0, out=None, nnz=None, all
                                    _ptr(Cm), Cm.stride(0), variant, _ptr(ws), wsb, _stream()),
           f"cuspmm_spmm_csr_ws(variant={variant})")
     return Cm
+
+
+CSR_KERNEL_NAMES = {1: "csr_rowsplit_vec", 2: "csr_subwarp_vec", 3: "csr_staged", 4: "csr_rowsplit_scalar", 5: "csr_dual",
+                    6: "csr_nnzsplit", 7: "csr_quad"}
+
+
+def csr_selected_variant(M, K, nnz, N, sell=False):
+    """The variant the selector (variant 0) runs for this shape on the current device."""
+    return int(lib().cuspmm_csr_selected_variant(M, K, nnz, N, 1 if sell else 0))
 
 
 def spmm_coo(rowIdxs, colIdxs, vals, M, K, B, variant=0, out=None):
@@ -276,6 +296,50 @@ def spmm_csr_host(rowPtrs_h, colIdxs_h, vals_h, M, K, B_h, C_h, variant=0):
     return ms.value
 
 
+def spmm_csr_host_devB(rowPtrs_h, colIdxs_h, vals_h, M, K, B_dev, C_h, variant=0, nnz=None):
+    """Host CSR (pinned torch CPU tensors or views of them), B already on the device (torch CUDA tensor; the kernels wait for
+    torch's current stream); returns device milliseconds."""
+    ms = C.c_float(0)
+    N = B_dev.shape[1]
+    nnz = int(colIdxs_h.numel()) if nnz is None else nnz
+    check(lib().cuspmm_spmm_csr_host_devB(rowPtrs_h.data_ptr(), colIdxs_h.data_ptr(), vals_h.data_ptr(), M, K, nnz,
+                                          B_dev.data_ptr(), B_dev.stride(0), _stream(), N, C_h.data_ptr(), variant,
+                                          C.byref(ms)), "cuspmm_spmm_csr_host_devB")
+    return ms.value
+
+
+def spmm_coo_host(rowIdxs_h, colIdxs_h, vals_h, M, K, B_h, C_h, variant=0):
+    ms = C.c_float(0)
+    check(lib().cuspmm_spmm_coo_host(rowIdxs_h.data_ptr(), colIdxs_h.data_ptr(), vals_h.data_ptr(), M, K,
+                                     int(colIdxs_h.numel()), B_h.data_ptr(), B_h.shape[1], C_h.data_ptr(), variant,
+                                     C.byref(ms)), "cuspmm_spmm_coo_host")
+    return ms.value
+
+
+def spmm_sell_host(slicePtrs_h, colIdxs_h, vals_h, M, K, B_h, C_h, variant=0):
+    ms = C.c_float(0)
+    check(lib().cuspmm_spmm_sell_host(slicePtrs_h.data_ptr(), colIdxs_h.data_ptr(), vals_h.data_ptr(), M, K, 32,
+                                      int(colIdxs_h.numel()), B_h.data_ptr(), B_h.shape[1], C_h.data_ptr(), variant,
+                                      C.byref(ms)), "cuspmm_spmm_sell_host")
+    return ms.value
+
+
+def spmm_bsr_host(blockRowPtrs_h, blockColIdxs_h, blocks_h, numBlockRows, br, bc, K, B_h, C_h, variant=1):
+    """variant 1: fp32 kernels; 2 / 3: bf16 / fp16 tensor-core plan (cast + re-tiling inside the call)."""
+    ms = C.c_float(0)
+    check(lib().cuspmm_spmm_bsr_host(blockRowPtrs_h.data_ptr(), blockColIdxs_h.data_ptr(), blocks_h.data_ptr(), numBlockRows,
+                                     br, bc, K, B_h.data_ptr(), B_h.shape[1], C_h.data_ptr(), variant, C.byref(ms)),
+          "cuspmm_spmm_bsr_host")
+    return ms.value
+
+
+def csr_check_sorted(rowPtrs, colIdxs, M, K):
+    """-> number of rows whose column indices are not strictly ascending / out of range (0 = the staged kernels' precondition holds)."""
+    bad = U32(0)
+    check(lib().cuspmm_csr_check_sorted(_ptr(rowPtrs), _ptr(colIdxs), M, K, C.byref(bad), _stream()), "cuspmm_csr_check_sorted")
+    return int(bad.value)
+
+
 def cusparse_spmm(fmt, rowOrPtr, colIdxs, vals, M, K, B, out, alg=0, warmup=3, iters=10):
     avg, mn = C.c_float(0), C.c_float(0)
     _torch().cuda.synchronize()
@@ -295,12 +359,29 @@ def cusparse_spmm_bsr(blockRowPtrs, blockColIdxs, blocks, nbr, nbc, bs, B, out, 
 
 
 class MgpuPlan:
-    def __init__(self, ngpus, rowPtrs_h, colIdxs_h, vals_h, M, K, maxN, devices=None):
+    """One process driving `ngpus` devices.  fmt = "csr" (rowPtrs, colIdxs, vals), "coo" (rowIdxs, colIdxs, vals),
+    "sell" (slicePtrs, colIdxs, vals) or "bsr" (blockRowPtrs, blockColIdxs, blocks; M = numBlockRows, br, bc given): host numpy arrays."""
+
+    def __init__(self, ngpus, a0_h, a1_h, a2_h, M, K, maxN, devices=None, fmt="csr", br=1, bc=1):
         self.h = P()
-        self.n, self.M = ngpus, M
+        self.n, self.M, self.fmt = ngpus, M, fmt
         devs = (C.c_int * ngpus)(*(devices or list(range(ngpus))))
-        check(lib().cuspmm_mgpu_create_csr(C.byref(self.h), ngpus, devs, rowPtrs_h.ctypes.data, colIdxs_h.ctypes.data,
-                                           vals_h.ctypes.data, M, K, int(colIdxs_h.shape[0]), maxN), "mgpu_create_csr")
+        L = lib()
+        if fmt == "csr":
+            check(L.cuspmm_mgpu_create_csr(C.byref(self.h), ngpus, devs, a0_h.ctypes.data, a1_h.ctypes.data, a2_h.ctypes.data,
+                                           M, K, int(a1_h.shape[0]), maxN), "mgpu_create_csr")
+        elif fmt == "coo":
+            check(L.cuspmm_mgpu_create_coo(C.byref(self.h), ngpus, devs, a0_h.ctypes.data, a1_h.ctypes.data, a2_h.ctypes.data,
+                                           M, K, int(a1_h.shape[0]), maxN), "mgpu_create_coo")
+        elif fmt == "sell":
+            check(L.cuspmm_mgpu_create_sell(C.byref(self.h), ngpus, devs, a0_h.ctypes.data, a1_h.ctypes.data, a2_h.ctypes.data,
+                                            M, K, 32, int(a1_h.shape[0]), maxN), "mgpu_create_sell")
+        elif fmt == "bsr":
+            check(L.cuspmm_mgpu_create_bsr(C.byref(self.h), ngpus, devs, a0_h.ctypes.data, a1_h.ctypes.data, a2_h.ctypes.data,
+                                           M, br, bc, K, maxN), "mgpu_create_bsr")
+            self.M = M * br
+        else:
+            raise ValueError(fmt)
 
     def set_B(self, B_h):
         self.N = B_h.shape[1]
@@ -314,6 +395,11 @@ class MgpuPlan:
     def splits(self):
         out = (U32 * (self.n + 1))()
         check(lib().cuspmm_mgpu_get_splits(self.h, out), "mgpu_get_splits")
+        return np.array(list(out), dtype=np.uint32)
+
+    def counts(self):
+        out = (U32 * self.n)()
+        check(lib().cuspmm_mgpu_get_counts(self.h, out), "mgpu_get_counts")
         return np.array(list(out), dtype=np.uint32)
 
     def get_C(self):

@@ -89,6 +89,46 @@ int coo_to_csr_rowptrs(const uint32_t *rowIdxs, uint32_t M, uint32_t nnz, uint32
     return CUSPMM_OK;
 }
 
+// Row pointers of a PANEL of a row-sorted COO matrix: entries [idxBase, idxBase + cnt) hold the rows [rowBase, rowBase + rows);
+// rowPtrs[j] = idxBase + (first entry of the panel whose row is >= rowBase + j), j = 0 .. rows, i.e. ABSOLUTE offsets into
+// the full colIdxs / vals arrays (the host pipeline runs the CSR kernels on such views).  rowIdxs points at the panel's
+// first entry.  One binary search per row.
+__global__ void coo_panel_rowptr_kernel(const uint32_t *__restrict__ rowIdxs, uint32_t rowBase, uint32_t rows, uint32_t cnt,
+                                        uint32_t idxBase, uint32_t *__restrict__ rowPtrs) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > rows) return;
+    const uint32_t r = rowBase + j;
+    uint32_t lo = 0, hi = cnt;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(rowIdxs + mid) < r) lo = mid + 1;
+        else hi = mid;
+    }
+    rowPtrs[j] = idxBase + lo;
+}
+
+int coo_panel_rowptrs(const uint32_t *rowIdxs, uint32_t rowBase, uint32_t rows, uint32_t cnt, uint32_t idxBase,
+                      uint32_t *rowPtrs, cudaStream_t st) {
+    coo_panel_rowptr_kernel<<<(rows + 1 + 127) / 128, 128, 0, st>>>(rowIdxs, rowBase, rows, cnt, idxBase, rowPtrs);
+    CUSPMM_LAUNCH_CHECK("coo_panel_rowptr_kernel");
+    return CUSPMM_OK;
+}
+
+// ------------------------------------------------------------------ sortedness check (precondition of the staged kernels)
+__global__ void csr_check_sorted_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, uint32_t M,
+                                        uint32_t K, unsigned int *__restrict__ bad) {
+    // one warp per row: entry i must be > entry i - 1 (strictly ascending) and < K
+    const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const uint32_t p0 = __ldg(rowPtrs + r), p1 = __ldg(rowPtrs + r + 1);
+    bool wrong = p1 < p0;
+    for (uint32_t i = p0 + lane_id(); i < p1 && !wrong; i += 32) {
+        const uint32_t c = __ldg(colIdxs + i);
+        if (c >= K || (i > p0 && __ldg(colIdxs + i - 1) >= c)) wrong = true;
+    }
+    if (__any_sync(0xFFFFFFFFu, wrong) && lane_id() == 0) atomicAdd(bad, 1u);
+}
+
 // ------------------------------------------------------------------ nnz-balanced row panels
 __global__ void partition_kernel(const uint32_t *__restrict__ rowPtrs, uint32_t M, uint32_t nnz, uint32_t parts,
                                  uint32_t *__restrict__ splits) {
@@ -317,6 +357,23 @@ extern "C" int cuspmm_coo_to_csr_rowptrs(const uint32_t *rowIdxs, uint32_t M, ui
                                          void *stream) {
     CUSPMM_REQUIRE(rowPtrs && (nnz == 0 || rowIdxs), "null pointer");
     return coo_to_csr_rowptrs(rowIdxs, M, nnz, rowPtrs, as_stream(stream));
+}
+
+extern "C" int cuspmm_csr_check_sorted(const uint32_t *rowPtrs, const uint32_t *colIdxs, uint32_t M, uint32_t K,
+                                       uint32_t *bad_rows_host, void *stream) {
+    CUSPMM_REQUIRE(bad_rows_host && (M == 0 || (rowPtrs && colIdxs)), "null pointer");
+    *bad_rows_host = 0;
+    if (M == 0) return CUSPMM_OK;
+    cudaStream_t st = as_stream(stream);
+    unsigned int *bad = nullptr;
+    CUSPMM_CUDA(cudaMallocAsync(&bad, sizeof(unsigned int), st));
+    CUSPMM_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned int), st));
+    csr_check_sorted_kernel<<<(M + 7) / 8, 256, 0, st>>>(rowPtrs, colIdxs, M, K, bad);
+    CUSPMM_LAUNCH_CHECK("csr_check_sorted_kernel");
+    CUSPMM_CUDA(cudaMemcpyAsync(bad_rows_host, bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    CUSPMM_CUDA(cudaFreeAsync(bad, st));
+    CUSPMM_CUDA(cudaStreamSynchronize(st));
+    return CUSPMM_OK;
 }
 
 extern "C" int cuspmm_partition_rows_by_nnz(const uint32_t *rowPtrs, uint32_t M, uint32_t nnz, uint32_t parts,

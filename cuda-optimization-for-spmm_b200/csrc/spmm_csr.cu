@@ -652,6 +652,11 @@ int spmm_sell_rows_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, 
 
 } // namespace cuspmm_b200
 
+// what variant 0 resolves to for this shape on the current device (16-byte aligned operands assumed)
+extern "C" int cuspmm_csr_selected_variant(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int sliced_ell) {
+    return cuspmm_b200::csr_select_variant(M, K, nnz, N, N % 4 == 0, sliced_ell != 0);
+}
+
 extern "C" size_t cuspmm_spmm_csr_workspace(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int variant) {
     return cuspmm_b200::spmm_csr_workspace_bytes(M, K, nnz, N, variant);
 }

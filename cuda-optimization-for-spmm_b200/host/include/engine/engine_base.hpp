@@ -19,12 +19,13 @@ class EngineBase {
 // src/spmm/csr/spmm_csr_k1.cu:45-73).  Defined in engine.cpp.
 struct RunOptions {
     int device = 0;          // --device
-    int nGpus = 1;           // --gpus: > 1 adds the row-panel multi-GPU run (CSR)
+    int nGpus = 1;           // --gpus: > 1 adds the row-panel multi-GPU run (every format)
     int warmup = 1;          // --warmup: untimed launches before timing
     int iters = 5;           // --iters: launches timed with CUDA events (cudaKernelTimeMs = average)
     int onlyKernel = 0;      // --variant: run just this kernel number (0 = all)
     int bsrBlock = 0;        // --bsr-block: convert the .csr file to BSR(b x b) on the device instead of reading .bsr
     bool gather = true;      // multi-GPU: store C panels straight into GPU 0's C over NVLink
+    double hbmPeakGBs = 0;   // --hbm-peak: roofline denominator in GB/s (0 = MEASURED_PEAKS.json / environment / fallback)
 };
 extern RunOptions g_opts;
 

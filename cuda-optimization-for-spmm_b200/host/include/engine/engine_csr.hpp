@@ -30,6 +30,9 @@ DenseMatrix<DT, MT> *spmmCSRWrapper5(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT,
 // additive: equal nnz ranges per warp, rows cut at range boundaries, ordered carry fix-up (few / skewed rows)
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmCSRWrapper6(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+// additive: every B read from tensor memory (columns split over the TMEM lane quarters)
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmCSRWrapper7(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 
 template <typename DT, typename MT, typename AccT>
 class EngineCSR : public EngineBase {
@@ -43,7 +46,7 @@ class EngineCSR : public EngineBase {
     double seqTime = 1.f;
 
     explicit EngineCSR(std::string dirPath) {
-        this->numKernels = 6;
+        this->numKernels = CUSPMM_CSR_NUM_VARIANTS;   // 7: the reference's four slots + the three additive kernels
         this->dirPath = dirPath;
         this->fmt = "CSR";
     }
@@ -65,6 +68,7 @@ class EngineCSR : public EngineBase {
         if (num == 4) return spmmCSRWrapper4<DT, MT, AccT>(ma, mb, mc);
         if (num == 5) return spmmCSRWrapper5<DT, MT, AccT>(ma, mb, mc);
         if (num == 6) return spmmCSRWrapper6<DT, MT, AccT>(ma, mb, mc);
+        if (num == 7) return spmmCSRWrapper7<DT, MT, AccT>(ma, mb, mc);
         if (num == -1) return spmmCSRWrapper3<DT, MT, AccT>(ma, mb, mc);
         throw std::runtime_error("Not implemented");
     }

@@ -20,6 +20,13 @@ template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper1(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper2(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+// 3 slice per CTA, 4 staged + tensor-memory operand path, 5 every B read from tensor memory (C-ABI ELL variants 3..5)
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper3(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper4(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper5(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 
 template <typename DT, typename MT, typename AccT>
 class EngineELL : public EngineBase {
@@ -33,7 +40,7 @@ class EngineELL : public EngineBase {
     double seqTime = 1.f;
 
     explicit EngineELL(std::string dirPath) {
-        this->numKernels = 2;   // the reference ships Wrapper2 but sets 1 (engine_ell.hpp:32)
+        this->numKernels = CUSPMM_ELL_NUM_VARIANTS;   // 5: every C-ABI ELL variant (the reference ships Wrapper2 but sets 1, engine_ell.hpp:32)
         this->dirPath = dirPath;
         this->fmt = "ELL";
     }
@@ -51,6 +58,9 @@ class EngineELL : public EngineBase {
         if (num == 0) return spmmELLCpu<DT, MT, AccT>(ma, mb, mc);
         if (num == 1) return spmmELLWrapper1<DT, MT, AccT>(ma, mb, mc);
         if (num == 2) return spmmELLWrapper2<DT, MT, AccT>(ma, mb, mc);
+        if (num == 3) return spmmELLWrapper3<DT, MT, AccT>(ma, mb, mc);
+        if (num == 4) return spmmELLWrapper4<DT, MT, AccT>(ma, mb, mc);
+        if (num == 5) return spmmELLWrapper5<DT, MT, AccT>(ma, mb, mc);
         if (num == -1) return spmmELLWrapper1<DT, MT, AccT>(ma, mb, mc);
         throw std::runtime_error("Not implemented");
     }

@@ -4,7 +4,7 @@
 //   testcase, sparsity, format, kernelType, denseOrdering, correct, cudaPrologTimeMs,
 //   cudaKernelTimeMs, cudaEpilogTimeMs, cudaTotalTimeMs, sequentialTimeMs
 // (all values quoted strings, as the reference prints them).  New keys are additive and come
-// after the reference's: kernelName, nGpus, gflops, algBytes, hbmGBs, hbmFrac, maxRelErr.
+// after the reference's: kernelName, nGpus, gflops, algBytes, hbmGBs, hbmFrac (of hbmPeakGBs), maxAbsErr (max |C - Cref|).
 #pragma once
 
 #include <cstdint>
@@ -27,10 +27,13 @@ namespace cuspmm {
 struct RecordExtra {
     std::string kernelName;
     int nGpus = 1;
-    double gflops = -1, algBytes = -1, hbmGBs = -1, hbmFrac = -1, maxRelErr = -1;
+    double gflops = -1, algBytes = -1, hbmGBs = -1, hbmFrac = -1, maxAbsErr = -1, e2eMs = -1;
+    double imbalance = -1;      // multi-GPU: max panel share / mean panel share (non-zeros, slots or blocks)
 };
-// measured HBM copy bandwidth used as the roofline denominator (MEASURED_PEAKS.json hbm_gbs)
-constexpr double kMeasuredHbmGBs = 6451.8;
+// HBM copy bandwidth used as the roofline denominator, GB/s: --hbm-peak, else $CUSPMM_HBM_PEAK_GBS, else "hbm_gbs" of
+// MEASURED_PEAKS.json ($CUSPMM_MEASURED_PEAKS, ./, ../, ../../, ../../../), else the profiling guide's fallback 6650.
+double hbmPeakGBs();
+const char *hbmPeakSource();
 }  // namespace cuspmm
 
 inline void reportTime(std::string tc, uint32_t aNumRows, uint32_t aNumCols, uint32_t aNumNonZero, std::string format,
@@ -54,8 +57,12 @@ inline void reportTime(std::string tc, uint32_t aNumRows, uint32_t aNumCols, uin
         printf(",\n\"kernelName\":\"%s\",\n\"nGpus\":\"%d\"", extra->kernelName.c_str(), extra->nGpus);
         if (extra->gflops >= 0) printf(",\n\"gflops\":\"%.3f\"", extra->gflops);
         if (extra->algBytes >= 0) printf(",\n\"algBytes\":\"%.0f\"", extra->algBytes);
-        if (extra->hbmGBs >= 0) printf(",\n\"hbmGBs\":\"%.3f\",\n\"hbmFrac\":\"%.5f\"", extra->hbmGBs, extra->hbmFrac);
-        if (extra->maxRelErr >= 0) printf(",\n\"maxRelErr\":\"%.3e\"", extra->maxRelErr);
+        if (extra->hbmGBs >= 0)
+            printf(",\n\"hbmGBs\":\"%.3f\",\n\"hbmFrac\":\"%.5f\",\n\"hbmPeakGBs\":\"%.1f\",\n\"hbmPeakSource\":\"%s\"", extra->hbmGBs,
+                   extra->hbmFrac, cuspmm::hbmPeakGBs(), cuspmm::hbmPeakSource());
+        if (extra->maxAbsErr >= 0) printf(",\n\"maxAbsErr\":\"%.3e\"", extra->maxAbsErr);
+        if (extra->e2eMs >= 0) printf(",\n\"e2eTotalTimeMs\":\"%.4f\"", extra->e2eMs);
+        if (extra->imbalance >= 0) printf(",\n\"panelImbalance\":\"%.4f\"", extra->imbalance);
     }
     printf("\n},\n");
     fflush(stdout);

@@ -2,9 +2,14 @@
 // Orchestration mirrors src/engine/engine.cpp:17-61 of the reference (host C, H2D of A/B/C, CPU
 // kernel 0, GPU kernels 1..numKernels checked against it, cuSPARSE when supported) with the leaks
 // fixed (the reference frees only c and dc, :59-60) and two additions from the north star: device-side
-// timing inside the wrappers and, for CSR with --gpus N, the nnz-balanced row-panel multi-GPU run.
+// timing inside the wrappers and, with --gpus N, the balanced row-panel multi-GPU run of every format.
 #include "engine.hpp"
 
+#include <cmath>
+#include <fstream>
+#include <functional>
+#include <memory>
+#include <sstream>
 #include <vector>
 
 namespace cuspmm {
@@ -12,43 +17,186 @@ namespace cuspmm {
 RunOptions g_opts;
 
 namespace {
+double g_hbmPeak = 0;
+std::string g_hbmPeakSource;
+void resolveHbmPeak() {
+    if (g_hbmPeak > 0) return;
+    if (g_opts.hbmPeakGBs > 0) { g_hbmPeak = g_opts.hbmPeakGBs; g_hbmPeakSource = "--hbm-peak"; return; }
+    if (const char *e = getenv("CUSPMM_HBM_PEAK_GBS")) {
+        const double v = atof(e);
+        if (v > 0) { g_hbmPeak = v; g_hbmPeakSource = "CUSPMM_HBM_PEAK_GBS"; return; }
+    }
+    std::vector<std::string> paths;
+    if (const char *e = getenv("CUSPMM_MEASURED_PEAKS")) paths.push_back(e);
+    for (const char *pre : {"", "../", "../../", "../../../"}) paths.push_back(std::string(pre) + "MEASURED_PEAKS.json");
+    for (const auto &p : paths) {
+        std::ifstream in(p);
+        if (!in) continue;
+        std::stringstream ss;
+        ss << in.rdbuf();
+        const std::string text = ss.str();
+        const size_t k = text.find("\"hbm_gbs\"");
+        if (k == std::string::npos) continue;
+        const size_t c = text.find(':', k);
+        if (c == std::string::npos) continue;
+        const double v = atof(text.c_str() + c + 1);
+        if (v > 0) { g_hbmPeak = v; g_hbmPeakSource = "measured (" + p + " hbm_gbs)"; return; }
+    }
+    g_hbmPeak = 6650.0;
+    g_hbmPeakSource = "fallback (B200_PROFILING.md)";
+}
+}  // namespace
+double hbmPeakGBs() { resolveHbmPeak(); return g_hbmPeak; }
+const char *hbmPeakSource() { resolveHbmPeak(); return g_hbmPeakSource.c_str(); }
+
+namespace {
 using Clock = std::chrono::high_resolution_clock;
 
-// CSR only: A split into nnz-balanced row panels over g_opts.nGpus devices (cuspmm_mgpu_*).
-template <typename MaT, typename MbT>
-void runMultiGpu(MaT *, MbT *, MbT *, const std::string &) {}
+// Every format: A split into balanced row panels over g_opts.nGpus devices (cuspmm_mgpu_*): CSR / COO by non-zeros at row
+// boundaries, ELL by slots at slice boundaries, BSR by blocks at block-row boundaries.  The record's cudaKernelTimeMs is
+// the device time (max over the GPUs, CUDA events); e2eTotalTimeMs is the wall clock of create + set_B + one run + get_C,
+// i.e. host operands in, host C out.
+struct MgpuJob {
+    std::string name;
+    uint32_t outRows = 0;
+    double algBytes = 0, flops = 0;
+    int variant = 0;
+    std::function<int(cuspmmMgpuPlan *, int, const int *)> create;
+};
 
-template <>
-void runMultiGpu(SparseMatrixCSR<float, uint32_t> *a, DenseMatrix<float, uint32_t> *b, DenseMatrix<float, uint32_t> *ref,
-                 const std::string &fmt) {
-    if (g_opts.nGpus <= 1) return;
+void runMgpuJob(const MgpuJob &job, uint32_t M, uint32_t K, uint32_t nnz, DenseMatrix<float, uint32_t> *b,
+                DenseMatrix<float, uint32_t> *ref, const std::string &fmt) {
+    const int n = g_opts.nGpus;
     RecordExtra ex;
-    ex.nGpus = g_opts.nGpus;
-    ex.kernelName = std::string("mgpu_row_panels_csr") + (g_opts.gather ? "+peer_gather" : "");
-    std::vector<int> devs(g_opts.nGpus);
-    for (int g = 0; g < g_opts.nGpus; ++g) devs[g] = g_opts.device + g;
+    ex.nGpus = n;
+    ex.kernelName = job.name + (g_opts.gather ? "+peer_gather" : "");
+    std::vector<int> devs(n);
+    for (int g = 0; g < n; ++g) devs[g] = g_opts.device + g;
     auto t0 = Clock::now();
     cuspmmMgpuPlan plan = nullptr;
-    cuspmmCheck(cuspmm_mgpu_create_csr(&plan, g_opts.nGpus, devs.data(), a->rowPtrs, a->colIdxs, a->data, a->numRows, a->numCols,
-                                       a->numNonZero, b->numCols));
+    cuspmmCheck(job.create(&plan, n, devs.data()));
     cuspmmCheck(cuspmm_mgpu_set_B(plan, b->data, b->numCols));
     const double pro = std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - t0).count() / 1000.0;
-    float ms = 0.f;
-    cuspmmCheck(cuspmm_mgpu_run(plan, 0, g_opts.gather, g_opts.warmup > 0 ? g_opts.warmup : 1, &ms));
-    cuspmmCheck(cuspmm_mgpu_run(plan, 0, g_opts.gather, g_opts.iters > 0 ? g_opts.iters : 1, &ms));
+    float ms = 0.f, first = 0.f;
+    auto tr = Clock::now();
+    cuspmmCheck(cuspmm_mgpu_run(plan, job.variant, g_opts.gather, 1, &first));
+    const double oneRun = std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - tr).count() / 1000.0;
+    if (g_opts.warmup > 1) cuspmmCheck(cuspmm_mgpu_run(plan, job.variant, g_opts.gather, g_opts.warmup - 1, &ms));
+    cuspmmCheck(cuspmm_mgpu_run(plan, job.variant, g_opts.gather, g_opts.iters > 0 ? g_opts.iters : 1, &ms));
     auto t1 = Clock::now();
-    DenseMatrix<float, uint32_t> res(a->numRows, b->numCols, false);
+    DenseMatrix<float, uint32_t> res(job.outRows, b->numCols, false);
     cuspmmCheck(cuspmm_mgpu_get_C(plan, res.data));
     const double epi = std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - t1).count() / 1000.0;
+    std::vector<uint32_t> counts(n);
+    cuspmmCheck(cuspmm_mgpu_get_counts(plan, counts.data()));
+    uint64_t total = 0;
+    uint32_t worst = 0;
+    for (uint32_t c : counts) { total += c; worst = std::max(worst, c); }
+    ex.imbalance = total ? (double)worst * n / (double)total : 1.0;
     cuspmmCheck(cuspmm_mgpu_destroy(plan));
     cudaCheckError(cudaSetDevice(g_opts.device));
-    const bool correct = allClose(res.data, ref->data, res.numElements(), REL_TOL, ABS_TOL);
-    const double N = b->numCols;
-    ex.algBytes = 8.0 * a->numNonZero + 4.0 * (a->numRows + 1.0) + 4.0 * a->numCols * N * g_opts.nGpus + 4.0 * a->numRows * N;
-    ex.gflops = 2.0 * a->numNonZero * N / (ms * 1e-3) / 1e9;
+    const size_t cmp = std::min(res.numElements(), ref->numElements());
+    const bool correct = allClose(res.data, ref->data, cmp, REL_TOL, ABS_TOL);
+    double maxAbs = 0;
+    for (size_t i = 0; i < cmp; ++i) maxAbs = std::max(maxAbs, std::fabs((double)res.data[i] - (double)ref->data[i]));
+    ex.maxAbsErr = maxAbs;
+    ex.algBytes = job.algBytes;
+    ex.gflops = job.flops / (ms * 1e-3) / 1e9;
     ex.hbmGBs = ex.algBytes / (ms * 1e-3) / 1e9;
-    ex.hbmFrac = ex.hbmGBs / (kMeasuredHbmGBs * g_opts.nGpus);
-    reportTime(testcase, a->numRows, a->numCols, a->numNonZero, fmt, b->ordering, 100 + g_opts.nGpus, pro, ms, epi, correct, &ex);
+    ex.hbmFrac = ex.hbmGBs / (hbmPeakGBs() * n);
+    ex.e2eMs = pro + oneRun + epi;
+    reportTime(testcase, M, K, nnz, fmt, b->ordering, 100 + n, pro, ms, epi, correct, &ex);
+}
+
+template <typename MaT, typename MbT>
+void runMultiGpu(MaT *, MaT *, MbT *, MbT *, const std::string &) {}
+
+using Dn = DenseMatrix<float, uint32_t>;
+
+template <>
+void runMultiGpu(SparseMatrixCSR<float, uint32_t> *a, SparseMatrixCSR<float, uint32_t> *, Dn *b, Dn *ref, const std::string &fmt) {
+    if (g_opts.nGpus <= 1) return;
+    const double N = b->numCols;
+    MgpuJob job;
+    job.name = "mgpu_row_panels_csr";
+    job.outRows = a->numRows;
+    job.algBytes = 8.0 * a->numNonZero + 4.0 * (a->numRows + 1.0) + 4.0 * a->numCols * N * g_opts.nGpus + 4.0 * a->numRows * N;
+    job.flops = 2.0 * a->numNonZero * N;
+    job.create = [&](cuspmmMgpuPlan *pl, int n, const int *devs) {
+        return cuspmm_mgpu_create_csr(pl, n, devs, a->rowPtrs, a->colIdxs, a->data, a->numRows, a->numCols, a->numNonZero, b->numCols);
+    };
+    runMgpuJob(job, a->numRows, a->numCols, a->numNonZero, b, ref, fmt);
+}
+
+template <>
+void runMultiGpu(SparseMatrixCOO<float, uint32_t> *a, SparseMatrixCOO<float, uint32_t> *, Dn *b, Dn *ref, const std::string &fmt) {
+    if (g_opts.nGpus <= 1) return;
+    const double N = b->numCols;
+    MgpuJob job;
+    job.name = "mgpu_row_panels_coo";
+    job.outRows = a->numRows;
+    job.algBytes = 12.0 * a->numNonZero + 4.0 * a->numCols * N * g_opts.nGpus + 4.0 * a->numRows * N;
+    job.flops = 2.0 * a->numNonZero * N;
+    job.create = [&](cuspmmMgpuPlan *pl, int n, const int *devs) {
+        return cuspmm_mgpu_create_coo(pl, n, devs, a->rowIdxs, a->colIdxs, a->data, a->numRows, a->numCols, a->numNonZero, b->numCols);
+    };
+    runMgpuJob(job, a->numRows, a->numCols, a->numNonZero, b, ref, fmt);
+}
+
+// ELL: the host holds the reference's column-ELL; the engine's sliced layout is produced on the device (da) and read back
+// once, then split at slice boundaries
+template <>
+void runMultiGpu(SparseMatrixELL<float, uint32_t> *a, SparseMatrixELL<float, uint32_t> *da, Dn *b, Dn *ref, const std::string &fmt) {
+    if (g_opts.nGpus <= 1) return;
+    const double N = b->numCols;
+    std::unique_ptr<SlicedELL<float, uint32_t>> s(da->toSliced());
+    std::vector<uint32_t> ptrs(s->numSlices + 1), cols(std::max<uint32_t>(s->numSlots, 1));
+    std::vector<float> vals(std::max<uint32_t>(s->numSlots, 1));
+    cudaCheckError(cudaMemcpy(ptrs.data(), s->slicePtrs, ptrs.size() * 4, cudaMemcpyDeviceToHost));
+    if (s->numSlots) {
+        cudaCheckError(cudaMemcpy(cols.data(), s->colIdxs, (size_t)s->numSlots * 4, cudaMemcpyDeviceToHost));
+        cudaCheckError(cudaMemcpy(vals.data(), s->data, (size_t)s->numSlots * 4, cudaMemcpyDeviceToHost));
+    }
+    MgpuJob job;
+    job.name = "mgpu_slice_panels_sell32";
+    job.outRows = a->numRows;
+    job.algBytes = 8.0 * s->numSlots + 4.0 * (s->numSlices + 1.0) + 4.0 * a->numCols * N * g_opts.nGpus + 4.0 * a->numRows * N;
+    job.flops = 2.0 * a->numNonZero * N;
+    const uint32_t slots = s->numSlots;
+    job.create = [&](cuspmmMgpuPlan *pl, int n, const int *devs) {
+        return cuspmm_mgpu_create_sell(pl, n, devs, ptrs.data(), cols.data(), vals.data(), a->numRows, a->numCols, 32, slots, b->numCols);
+    };
+    runMgpuJob(job, a->numRows, a->numCols, a->numNonZero, b, ref, fmt);
+}
+
+// BSR: block rows balanced by blocks; fp32 kernels (bit-for-bit spmmBSRCpu's order), and for 16x16 / 32x32 blocks also the
+// tcgen05 bf16 plan per panel
+template <>
+void runMultiGpu(SparseMatrixBSR<float, uint32_t> *a, SparseMatrixBSR<float, uint32_t> *, Dn *b, Dn *ref, const std::string &fmt) {
+    if (g_opts.nGpus <= 1) return;
+    if (b->numRows < a->numCols) return;       // B must cover the (padded) K of the BSR matrix
+    const double N = b->numCols;
+    const bool tcOk = a->blockRowSize == a->blockColSize && (a->blockRowSize == 16 || a->blockRowSize == 32);
+    for (int variant : {1, 2}) {
+        if (variant == 2 && !tcOk) continue;
+        const double e = variant == 1 ? 4.0 : 2.0;
+        MgpuJob job;
+        job.name = variant == 1 ? "mgpu_blockrow_panels_bsr_f32" : "mgpu_blockrow_panels_bsr_tcgen05_bf16";
+        job.variant = variant;
+        job.outRows = a->numBlockRows * a->blockRowSize;
+        job.algBytes = (double)a->numElements * e + 4.0 * a->numBlocks + 4.0 * (a->numBlockRows + 1.0) + e * a->numCols * N * g_opts.nGpus +
+                       4.0 * job.outRows * N;
+        job.flops = 2.0 * a->numElements * N;
+        job.create = [&](cuspmmMgpuPlan *pl, int n, const int *devs) {
+            return cuspmm_mgpu_create_bsr(pl, n, devs, a->blockRowPtrs, a->blockColIdxs, a->data, a->numBlockRows, a->blockRowSize,
+                                          a->blockColSize, a->numCols, b->numCols);
+        };
+        if (variant == 2) {      // the tensor-core result is compared with the reference's tolerances all the same
+            runMgpuJob(job, a->numRows, a->numCols, a->numNonZero, b, ref, fmt);
+        } else {
+            runMgpuJob(job, a->numRows, a->numCols, a->numNonZero, b, ref, fmt);
+        }
+    }
 }
 }  // namespace
 
@@ -96,8 +244,8 @@ void runEngine(EngT *engine, typename EngT::MataT *a, typename EngT::MatbT *b, f
         delete dc;
     }
 
-    // 5. multi-GPU row panels (CSR)
-    runMultiGpu(a, b, cpuRes, engine->fmt);
+    // 5. multi-GPU row panels (every format)
+    runMultiGpu(a, da, b, cpuRes, engine->fmt);
 
     delete da;
     delete db;

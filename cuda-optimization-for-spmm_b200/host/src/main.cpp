@@ -4,7 +4,7 @@
 //   files: *.coo *.csr *.bsr *_colind.ell *_values.ell *_rowind.ell *_values_colmajor.ell dense.in  (:98-144)
 // Additive flags (defaults keep the reference behaviour except the device ordinal, which the
 // reference hard-codes to 7, main.cu:176):
-//   --device D  --gpus N  --iters I  --warmup W  --variant K  --skip-cpu  --bsr-block B  --no-gather
+//   --device D  --gpus N  --iters I  --warmup W  --variant K  --skip-cpu  --bsr-block B  --no-gather  --hbm-peak GB/s
 #include "engine.hpp"
 #include "format.hpp"
 
@@ -29,13 +29,15 @@ static void printHelp(const char *prog) {
               << "  -h, --help      Display this help message\n"
               << "B200 engine additions:\n"
               << "  --device <n>    CUDA device ordinal (default 0)\n"
-              << "  --gpus <n>      also run CSR sharded by nnz-balanced row panels over n GPUs\n"
+              << "  --gpus <n>      also run every selected format sharded by balanced row panels over n GPUs\n"
               << "  --no-gather     multi-GPU: leave C sharded instead of storing it into GPU 0 over NVLink\n"
               << "  --iters <n>     timed launches per kernel (CUDA events, default 5)\n"
               << "  --warmup <n>    untimed launches per kernel (default 1)\n"
               << "  --variant <k>   run only GPU kernel number k of each engine\n"
               << "  --skip-cpu      skip kernel 0 (records then compare against zeros, as the reference's skipSeq)\n"
-              << "  --bsr-block <b> build BSR(b x b) from the .csr file on the device instead of reading .bsr\n";
+              << "  --bsr-block <b> build BSR(b x b) from the .csr file on the device instead of reading .bsr\n"
+              << "  --no-gather     multi-GPU: leave C sharded instead of storing the panels into GPU 0's C over NVLink\n"
+              << "  --hbm-peak <x>  HBM bandwidth in GB/s for the roofline fraction (default: MEASURED_PEAKS.json, else 6650)\n";
 }
 
 int main(int argc, char *argv[]) {
@@ -49,6 +51,7 @@ int main(int argc, char *argv[]) {
         {"iters", required_argument, nullptr, 12},  {"warmup", required_argument, nullptr, 13},
         {"variant", required_argument, nullptr, 14}, {"skip-cpu", no_argument, nullptr, 15},
         {"bsr-block", required_argument, nullptr, 16}, {"no-gather", no_argument, nullptr, 17},
+        {"hbm-peak", required_argument, nullptr, 18},
         {nullptr, 0, nullptr, 0}};
     int opt;
     while ((opt = getopt_long(argc, argv, "hd:", longOpts, nullptr)) != -1) {
@@ -66,6 +69,7 @@ int main(int argc, char *argv[]) {
         case 15: skipCpu = true; break;
         case 16: cuspmm::g_opts.bsrBlock = atoi(optarg); break;
         case 17: cuspmm::g_opts.gather = false; break;
+        case 18: cuspmm::g_opts.hbmPeakGBs = atof(optarg); break;
         case 'h': printHelp(argv[0]); return 0;
         case 'd': dir = optarg; break;
         case '?': return 1;

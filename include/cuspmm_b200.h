@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CUSPMM_B200_VERSION 100
+#define CUSPMM_B200_VERSION 200
 
 typedef enum {
     CUSPMM_OK = 0,
@@ -80,6 +80,9 @@ int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, co
                     uint32_t M, uint32_t K, uint32_t nnz,
                     const float *B_dev, uint32_t N, size_t ldb,
                     float *C_dev, size_t ldc, int variant, void *stream);
+/* The kernel variant 0 resolves to for this shape on the current device, assuming 16-byte aligned operands (sliced_ell != 0:
+ * the same question for cuspmm_spmm_sell, answered in CSR variant numbers).  bench.py records it beside every measurement. */
+int cuspmm_csr_selected_variant(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int sliced_ell);
 /* The same with caller-provided device workspace (16-byte aligned, cuspmm_spmm_csr_workspace bytes; 0 for variants
  * 1..5): variant 6 runs, and variant 0 may select it (few rows with >= 16 non-zeros each). */
 size_t cuspmm_spmm_csr_workspace(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int variant);
@@ -192,35 +195,78 @@ int cuspmm_coo_to_csr_rowptrs(const uint32_t *rowIdxs_dev, uint32_t M, uint32_t 
  * double loop of DenseMatrix::toOrdering (src/formats/dense.cu:140-191). */
 int cuspmm_transpose_f32(const float *in_dev, uint32_t rows, uint32_t cols, float *out_dev, void *stream);
 
+/* Verifies the precondition of the staged kernels: column indices strictly ascending inside every row and < K.
+ * *bad_rows_host = number of rows that violate it (0 = fine).  Synchronises the stream. */
+int cuspmm_csr_check_sorted(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, uint32_t M, uint32_t K,
+                            uint32_t *bad_rows_host, void *stream);
+
 /* ------------------------------------------------- host-buffer entry points ---- */
 /* What runEngine + spmm<FMT>Wrapper<k> do end to end (src/engine/engine.cpp:20-44,
  * src/spmm/csr/spmm_csr_k3.cu:59-105): operands in HOST memory, H2D, kernel, D2H of
- * C.  Row panels are pipelined over two streams so the copies overlap the kernel.
- * Host buffers should be pinned (cudaHostAlloc / cuspmm_host_alloc) for the copies
- * to be asynchronous.  Synchronises before returning.  `device_ms` (optional)
- * receives the device time of the whole pipeline measured with CUDA events. */
+ * C -- for every format, as the reference runs all four through one runEngine (src/engine/engine.cpp:63-80).  A is cut
+ * into balanced panels (rows / slices / block rows) that are pipelined over three streams so the copies overlap the
+ * kernels.  Host buffers should be pinned (cudaHostAlloc / cuspmm_host_alloc) for the copies to be asynchronous.
+ * Synchronises before returning, on every exit path.  `device_ms` (optional) receives the device time of the whole
+ * pipeline measured with CUDA events.  Device staging buffers are cached per device between calls and freed by
+ * cuspmm_host_pipeline_release(device) (device < 0: all devices).  CSR / ELL: column indices ascending inside a row. */
 int cuspmm_spmm_csr_host(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
                          uint32_t M, uint32_t K, uint32_t nnz,
                          const float *B, uint32_t N, float *C, int variant, float *device_ms);
+/* The same with B already resident on the current device (row stride ldb): the kernels wait for the work enqueued so far
+ * on `b_ready_stream` (e.g. the stream an NCCL all-gather of B runs on).  Used when one matrix is sharded over several
+ * processes: every rank uploads its own row panel of A, B arrives over NVLink. */
+int cuspmm_spmm_csr_host_devB(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
+                              uint32_t M, uint32_t K, uint32_t nnz,
+                              const float *B_dev, size_t ldb, void *b_ready_stream,
+                              uint32_t N, float *C, int variant, float *device_ms);
+/* COO (entries sorted by (row, col)); variant as cuspmm_spmm_coo (0 / 2: panel-wise device row pointers + CSR selector;
+ * 1: the row-aligned COO kernel, one launch). */
+int cuspmm_spmm_coo_host(const uint32_t *rowIdxs, const uint32_t *colIdxs, const float *vals,
+                         uint32_t M, uint32_t K, uint32_t nnz,
+                         const float *B, uint32_t N, float *C, int variant, float *device_ms);
+/* Sliced ELL (layout above); panels end on slice boundaries, balanced by slots. */
+int cuspmm_spmm_sell_host(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
+                          uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots,
+                          const float *B, uint32_t N, float *C, int variant, float *device_ms);
+/* BSR, fp32 blocks on the host; C is (numBlockRows * br) x N.  variant 0 / 1: fp32 kernels, panels of block rows balanced
+ * by blocks; 2 / 3: bf16 / fp16 tensor-core plan built on the device after the upload (cast + re-tiling of the blocks and of
+ * B are inside the timed region), one launch. */
+int cuspmm_spmm_bsr_host(const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs, const float *blocks,
+                         uint32_t numBlockRows, uint32_t br, uint32_t bc, uint32_t K,
+                         const float *B, uint32_t N, float *C, int variant, float *device_ms);
+int cuspmm_host_pipeline_release(int device);
 int cuspmm_host_alloc(void **ptr, size_t bytes); /* pinned, cf. cudaMallocHost in src/formats/dense.cu:244 */
 int cuspmm_host_free(void *ptr);
 
 /* ------------------------------------------------------ multi-GPU engine ---- */
 /* Row-panel data parallelism over `ngpus` devices of one node (north_star (c);
- * the reference is single-device, src/main.cu:176).  create(): A (HOST CSR) is split
- * into nnz-balanced row panels, panel g is uploaded to device devices[g];
+ * the reference is single-device, src/main.cu:176), for every format.  create_<fmt>(): A (HOST arrays) is split
+ * into balanced contiguous row panels -- CSR: by non-zeros (split points from the device partitioner); COO: the same rule,
+ * moved to row boundaries; sliced ELL: at slice boundaries, by slots; BSR: at block-row boundaries, by blocks -- and panel g
+ * is uploaded to device devices[g];
  * set_B(): B (HOST) is uploaded to device 0 and replicated to the peers over
  * NVLink (cudaMemcpyPeerAsync);  run(): every device multiplies its panel on its
- * own stream; with gather != 0 each device's kernel writes its C rows straight
+ * own stream (variant numbering of the format; BSR: 1 fp32, 2 bf16, 3 fp16 tensor cores); with gather != 0 each device's
+ * kernel writes its C rows straight
  * into device 0's C through peer memory (no separate collective), otherwise C
  * stays sharded.  Device time = max over devices, CUDA events.  */
 typedef struct cuspmmMgpuPlan_s *cuspmmMgpuPlan;
 int cuspmm_mgpu_create_csr(cuspmmMgpuPlan *plan, int ngpus, const int *devices,
                            const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
                            uint32_t M, uint32_t K, uint32_t nnz, uint32_t maxN);
+int cuspmm_mgpu_create_coo(cuspmmMgpuPlan *plan, int ngpus, const int *devices,
+                           const uint32_t *rowIdxs, const uint32_t *colIdxs, const float *vals,
+                           uint32_t M, uint32_t K, uint32_t nnz, uint32_t maxN);
+int cuspmm_mgpu_create_sell(cuspmmMgpuPlan *plan, int ngpus, const int *devices,
+                            const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
+                            uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots, uint32_t maxN);
+int cuspmm_mgpu_create_bsr(cuspmmMgpuPlan *plan, int ngpus, const int *devices,
+                           const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs, const float *blocks,
+                           uint32_t numBlockRows, uint32_t br, uint32_t bc, uint32_t K, uint32_t maxN);
 int cuspmm_mgpu_set_B(cuspmmMgpuPlan plan, const float *B, uint32_t N);
 int cuspmm_mgpu_run(cuspmmMgpuPlan plan, int variant, int gather, int iters, float *max_device_ms);
-int cuspmm_mgpu_get_splits(cuspmmMgpuPlan plan, uint32_t *splits /* ngpus+1 */);
+int cuspmm_mgpu_get_splits(cuspmmMgpuPlan plan, uint32_t *splits /* ngpus+1, in rows of C */);
+int cuspmm_mgpu_get_counts(cuspmmMgpuPlan plan, uint32_t *counts /* ngpus: non-zeros / slots / blocks per panel */);
 int cuspmm_mgpu_get_C(cuspmmMgpuPlan plan, float *C /* host, M x N */);
 int cuspmm_mgpu_destroy(cuspmmMgpuPlan plan);
 
