@@ -180,7 +180,7 @@ def reference_arm(args, orc, np):
     exec(text[text.index("NAMED = {"):text.index("def gen_csr_device")], ns)
     M, K, density, N = ns["NAMED"][args.workload]
     threads = os.cpu_count() or 1
-    rows_cap = min(M, 64 * threads)
+    rows_cap = min(M, 256 * threads)
     rp, ci, va = numpy_csr_rows(np, K, density, rows_cap, 618)
     B = np.random.default_rng(619).uniform(-1, 1, size=(K, N)).astype(np.float32)
     a = orc.CSR(rows_cap, K, rp, ci, va)
@@ -710,7 +710,7 @@ def main():
     if world == 1 and rank == 0:
         try:
             threads = os.cpu_count() or 1
-            rows_cap = min(M, 64 * threads)
+            rows_cap = min(M, 256 * threads)
             srp, sci, sva = wl.csr_sample_to_host(rp_l, ci_l, va_l, 0, rows_cap)
             a_host = orc.CSR(rows_cap, K, srp, sci, sva)
             B_host = Bd.cpu().numpy()

@@ -127,19 +127,23 @@ def test_csr_host_devB_entry(b):
     assert rel_err(C_h, ref, den) <= TOL
 
 
-def test_csr_host_many_panels(b):
-    """Enough rows and bytes for the maximum panel count (the event arrays hold exactly that many)."""
+def test_csr_host_many_panels(b, wl):
+    """Enough rows and bytes for the MAXIMUM panel count of the host pipeline (16: >= 512 MiB of (col, val) and >= 16 x 6400
+    rows); the 'one more tapered panel' rule used to push it to 17, past the event arrays."""
     import torch
-    M, K, N = 120000, 600, 128
-    a = random_csr(M, K, 0.4, seed=51)           # 28.8 M nnz = 230 MB of (col, val)
-    assert a.nnz * 8 >= 7 * (32 << 20)
-    B = np.random.default_rng(52).uniform(-1, 1, (K, N)).astype(np.float32)
+    M, K, N = 110000, 1500, 128
+    rp, ci, va = wl.gen_csr_device(M, K, 0.41, seed=51)
+    nnz = int(ci.numel())
+    assert nnz * 8 >= 16 * (32 << 20)
+    Bd = wl.gen_dense_device(K, N, seed=52)
     C_h = torch.empty((M, N), dtype=torch.float32).pin_memory()
-    b.spmm_csr_host(b.pinned(a.rowPtrs), b.pinned(a.colIdxs), b.pinned(a.vals), M, K, b.pinned(B), C_h)
-    rows = slice(M - 300, M)
-    sub = orc.CSR(300, K, (a.rowPtrs[M - 300:] - a.rowPtrs[M - 300]).astype(np.uint32),
-                  a.colIdxs[a.rowPtrs[M - 300]:], a.vals[a.rowPtrs[M - 300]:])
-    assert orc.max_rel_err(C_h[rows].numpy(), orc.spmm_csr(sub, B), orc.absprod_csr(sub, B)) <= TOL
+    ms = b.spmm_csr_host(rp.cpu().pin_memory(), ci.cpu().pin_memory(), va.cpu().pin_memory(), M, K, Bd.cpu().pin_memory(), C_h)
+    assert ms > 0
+    Bh = Bd.cpu().numpy()
+    for r0 in (0, M // 2, M - 64):
+        srp, sci, sva = wl.csr_sample_to_host(rp, ci, va, r0, r0 + 64)
+        sub = orc.CSR(64, K, srp, sci, sva)
+        assert orc.max_rel_err(C_h[r0:r0 + 64].numpy(), orc.spmm_csr(sub, Bh), orc.absprod_csr(sub, Bh)) <= TOL
 
 
 @pytest.mark.parametrize("bs,variant", [(16, 1), (16, 2), (32, 3), (4, 1)])
