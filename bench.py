@@ -327,6 +327,12 @@ def bsr_case(cx, M, K, density, N, bs, seed, steps, dtype="bf16"):
         tmp = torch.empty_like(Cd)
         avg, mn = b.cusparse_spmm_bsr(brp, bci, blocks, nbr, nbc, bs, Bd, tmp, warmup=1, iters=3)
         rec["cusparse"] = {"alg": "BSR fp32 ALG_DEFAULT", "ms_avg": avg, "speedup_vs_cusparse": avg / ms}
+        try:
+            avg, mn, w = b.cusparse_spmm_blockedell(brp, bci, blocks, nbr, nbc, bs, Bd, tmp, warmup=1, iters=3)
+            rec["cusparse_blocked_ell"] = {"alg": "BLOCKED_ELL_ALG1 fp32", "ms_avg": avg, "speedup_vs_cusparse": avg / ms,
+                                           "ell_width_blocks": w, "padding_factor": w * nbr / max(nb, 1)}
+        except Exception as ex:
+            rec["cusparse_blocked_ell"] = {"error": str(ex)[:160]}
         del tmp
     except Exception as ex:
         rec["cusparse"] = {"error": str(ex)[:160]}

@@ -65,6 +65,8 @@ def lib():
                                            C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.cuspmm_cusparse_spmm_bsr.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, P, C.c_int, C.c_int,
                                                C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.cuspmm_cusparse_spmm_blockedell.argtypes = [P, P, P, U32, U32, U32, U32, P, U32, P, C.c_int, C.c_int,
+                                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(U32)]
         L.cuspmm_mgpu_create_csr.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32]
         L.cuspmm_mgpu_create_coo.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32]
         L.cuspmm_mgpu_create_sell.argtypes = [C.POINTER(P), C.c_int, C.POINTER(C.c_int), P, P, P, U32, U32, U32, U32, U32]
@@ -356,6 +358,16 @@ def cusparse_spmm_bsr(blockRowPtrs, blockColIdxs, blocks, nbr, nbc, bs, B, out, 
                                          int(blockColIdxs.numel()), bs, _ptr(B), B.shape[1], _ptr(out), warmup, iters,
                                          C.byref(avg), C.byref(mn)), "cuspmm_cusparse_spmm_bsr")
     return avg.value, mn.value
+
+
+def cusparse_spmm_blockedell(blockRowPtrs, blockColIdxs, blocks, nbr, nbc, bs, B, out, warmup=2, iters=5):
+    """-> (avg ms, min ms, padded width in blocks) of cuSPARSE's Blocked-ELL SpMM on the BSR operand padded to its longest block row."""
+    avg, mn, w = C.c_float(0), C.c_float(0), U32(0)
+    _torch().cuda.synchronize()
+    check(lib().cuspmm_cusparse_spmm_blockedell(_ptr(blockRowPtrs), _ptr(blockColIdxs), _ptr(blocks), nbr, nbc,
+                                                int(blockColIdxs.numel()), bs, _ptr(B), B.shape[1], _ptr(out), warmup, iters,
+                                                C.byref(avg), C.byref(mn), C.byref(w)), "cuspmm_cusparse_spmm_blockedell")
+    return avg.value, mn.value, int(w.value)
 
 
 class MgpuPlan:

@@ -22,16 +22,20 @@
 // Per C element the terms are added in ascending-column (= storage) order with one IEEE fma each: bit-identical to
 // variants 1-5.  Column indices must ascend inside a row (cuspmm_b200.h).
 //
-// A side: no 32-entry register windows (8 rows x 2 registers would not fit) and no per-chunk entry counts (their uniform-
-// datapath bookkeeping cost more issue slots than the FMAs: first version, profiles/r02_ncu_quad_v1_summary.txt).  A warp
-// keeps, per row, a look-ahead of the next L = 4 entries (lane = 4 * row + entry: ONE 32-lane load covers its 8 rows) and
-// consumes rows in FIXED batches of four entries, independent of chunk boundaries: the TMEM ring is a sliding window of the
-// last (up to) 128 rows of B, [rel * 32, have * 32); a row whose four look-ahead columns all lie below the window's end runs
-// one straight-line batch (2 warp-uniform LDS.128 of (TMEM address, value) pairs parked in a 256-byte scratch, 4 tcgen05.ld
-// in flight, one wait, 8 FFMA2) and advances by four; a stage is released once the smallest look-ahead column of the warp
-// (one REDUX) has left it.  Row tails (< 4 entries left) and rows whose next four entries do not fit into a full window
-// (very sparse rows) take an exact-count path.  The loads of a row's next look-ahead are issued before its entries are
-// processed.
+// A side: no 32-entry register windows (8 rows x 2 registers would not fit): every visit of a chunk a warp loads, per
+// row, the next L = 8 entries (lane = 8 * row + entry: two 32-lane loads cover the 8 rows), counts by ballot how many fall
+// into the chunk (a prefix: ascending columns), parks (TMEM address, value) pairs in a 512-byte shared-memory scratch of
+// its own and reads them back as warp-uniform LDS.128 broadcasts (two entries each).  The loads for the NEXT visit are
+// issued before the current entries are processed.  A row with 8 or more entries inside one chunk makes the warp visit the
+// chunk again (dense rows: every visit is full, the overhead is amortised).
+//
+// Measured (profiles/r02_ncu_quad_v1_v2_v3_summary.txt): bit-identical to variants 1-5 on every shape tried, shared-memory
+// wavefronts 0.44 G instead of 0.90 G (dual) / 1.19 G (staged) on large_25605 -- but 4.75 ms against 4.13 ms for the dual-path
+// kernel: four warps share every non-zero, each paying the per-row control flow for 2 FFMA2 of payload, so the kernel
+// executes 3.6 G warp instructions (dual: 2.8 G) and is bound by issue slots (68 %) before the tcgen05.ld rate.  Two
+// restructurings of the consumer loop (fixed batches of four entries on a sliding window; one visit per acquired stage)
+// were slower still (5.2-5.9 ms; git history of this file).  The selector therefore never picks this variant; it stays
+// callable (CSR variant 7 / ELL variant 5) and tested as the reference point for that design.
 #include "tmem_common.cuh"
 
 namespace cuspmm_b200 {
@@ -43,11 +47,12 @@ __device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t desc) 
     asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(desc) : "memory");
 }
 
-// NG groups of 4 consumer warps (8 rows each), NI issuer warps (issuer 0 also drives the TMA ring)
-template <int NG, int NI, int STAGES = 3>
+// NG groups of 4 consumer warps (8 rows each), NI issuer warps (issuer 0 also drives the TMA ring), HB = TMEM loads in
+// flight per wait (2 or 4)
+template <int NG, int NI, int HB = 4, int STAGES = 3>
 struct QuadCfg {
-    static constexpr int kNG = NG, kNI = NI, kStages = STAGES;
-    static constexpr int kRW = 8, kL = 4, kKC = 32, kTS = 4;
+    static constexpr int kNG = NG, kNI = NI, kHB = HB, kStages = STAGES;
+    static constexpr int kRW = 8, kL = 8, kKC = 32, kTS = 4;
     static constexpr int kNC = NG * 4;                      // consumer warps
     static constexpr int kRows = NG * kRW;
     static constexpr int kThreads = (kNC + NI) * 32;
@@ -58,6 +63,7 @@ struct QuadCfg {
     static constexpr size_t kSmemBytes = (size_t)kStageBytes * STAGES + (size_t)kScratchBytes * kNC +
                                          (2 * STAGES + 2 * kTS) * sizeof(uint64_t) + 16 + 128;
     static_assert(kThreads <= 1024 && kSmemBytes <= 232448, "CTA limits");
+    static_assert(HB == 2 || HB == 4, "HB");
 };
 
 // CNT (1..4) consecutive entries of one row: (TMEM address, value) pairs at shared address sp (warp-uniform LDS
@@ -140,13 +146,18 @@ __device__ __forceinline__ void row_batch<4>(float2 (&acc)[2], uint32_t sp) {
     fma_entry(acc, v2, b[8], b[9], b[10], b[11]);
     fma_entry(acc, v3, b[12], b[13], b[14], b[15]);
 }
-// n (1..4, warp-uniform) entries at sp: the exact-count path of row tails and of rows that do not fit into the window
+// n (1..HB, warp-uniform) entries at sp
 template <int HB>
 __device__ __forceinline__ void row_entries(float2 (&acc)[2], uint32_t sp, uint32_t n) {
-    if (n >= 4) row_batch<4>(acc, sp);
-    else if (n == 3) row_batch<3>(acc, sp);
-    else if (n == 2) row_batch<2>(acc, sp);
-    else row_batch<1>(acc, sp);
+    if constexpr (HB == 4) {
+        if (n >= 4) row_batch<4>(acc, sp);
+        else if (n == 3) row_batch<3>(acc, sp);
+        else if (n == 2) row_batch<2>(acc, sp);
+        else row_batch<1>(acc, sp);
+    } else {
+        if (n >= 2) row_batch<2>(acc, sp);
+        else row_batch<1>(acc, sp);
+    }
 }
 
 template <class CFG, bool SELL>
@@ -156,10 +167,10 @@ csr_quad_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
                 const float *__restrict__ B, size_t ldb, float *__restrict__ C, size_t ldc,
                 const __grid_constant__ CUtensorMap tmapB, int useTmap) {
     constexpr int NC = CFG::kNC, NI = CFG::kNI, RW = CFG::kRW, L = CFG::kL, KC = CFG::kKC, TS = CFG::kTS;
-    constexpr int STAGES = CFG::kStages, NS = CFG::kSlots;
+    constexpr int STAGES = CFG::kStages, NS = CFG::kSlots, HB = CFG::kHB;
     constexpr uint32_t kStageBytes = CFG::kStageBytes, kRowBytes = CFG::kRowBytes;
     constexpr uint32_t STEP = SELL ? 32u : 1u;              // distance between consecutive entries of a row
-    static_assert(RW == 8 && L == 4 && NS == 1, "the lane <-> (row, entry) mapping below is written for 8 rows x 4 entries");
+    static_assert(RW == 8 && L == 8 && NS == 2, "the lane <-> (row, entry) mapping below is written for 8 x 8");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *ring = smem_raw;
     unsigned char *scratch = smem_raw + (size_t)kStageBytes * STAGES;
@@ -266,97 +277,86 @@ csr_quad_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict
         uint2 *sc = reinterpret_cast<uint2 *>(scratch + (size_t)warp * CFG::kScratchBytes);
         uint32_t sc_sa = smem_u32(sc);
         asm volatile("" : "+r"(sc_sa));
-        // lane l: entry (l & 3) of the look-ahead of row (l >> 2)
-        uint32_t cur = 0, endp = 0, ecol = kPad;
-        float eval = 0.f;
+        // slot s, lane l: entry (l & 7) of the look-ahead of row 4 s + (l >> 3)
+        uint32_t cur[NS], endp[NS], ecol[NS];
+        float eval[NS];
         float2 acc[RW][2];                     // acc[i] = columns 128 q + 4 lane .. + 3 of row i
 #pragma unroll
         for (int i = 0; i < RW; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
-        auto fetch = [&]() {
-            ecol = kPad;
-            eval = 0.f;
-            if (cur < endp) {
-                ecol = __ldg(colIdxs + cur);
-                eval = __ldg(vals + cur);
+        auto fetch = [&](int s) {
+            ecol[s] = kPad;
+            eval[s] = 0.f;
+            if (cur[s] < endp[s]) {
+                ecol[s] = __ldg(colIdxs + cur[s]);
+                eval[s] = __ldg(vals + cur[s]);
             }
         };
-        {
-            const uint32_t r = rbase + (lane >> 2);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const uint32_t r = rbase + s * 4 + (lane >> 3);
+            cur[s] = endp[s] = 0;
             if (r < rowEnd) {
                 if constexpr (SELL) {
                     const uint32_t sb = __ldg(rowPtrs + (r >> 5));
                     const uint32_t w = (__ldg(rowPtrs + (r >> 5) + 1) - sb) >> 5;      // slice width in slots
-                    cur = sb + (r & 31u) + (lane & 3u) * 32u;
-                    endp = sb + (r & 31u) + w * 32u;
+                    cur[s] = sb + (r & 31u) + (lane & 7u) * 32u;
+                    endp[s] = sb + (r & 31u) + w * 32u;
                 } else {
-                    cur = __ldg(rowPtrs + r) + (lane & 3u);
-                    endp = __ldg(rowPtrs + r + 1);
+                    cur[s] = __ldg(rowPtrs + r) + (lane & 7u);
+                    endp[s] = __ldg(rowPtrs + r + 1);
                 }
             }
-            fetch();
+            fetch(s);
         }
 
-        uint32_t have = 0, rel = 0;            // stages acquired / released: B rows [rel * KC, have * KC) are in the ring
-        bool busy = false;                     // the last visit found work for most rows: visit again before growing the window
-        while (true) {
-            // every unprocessed entry of this warp has a column >= minc (ascending columns; finished rows / padding: kPad)
-            const uint32_t minc = __reduce_min_sync(0xFFFFFFFFu, ecol);
-            if (rel < have && (rel + 1) * KC <= minc) {
-                tc_fence_before();
-                do {
-                    if (lane == 0) mbar_arrive(t_empty + rel % TS);
-                    ++rel;
-                } while (rel < have && (rel + 1) * KC <= minc);
-            }
-            if (rel == nchunks) break;
-            // One visit per acquired stage: a row needs its next four entries inside the window, which grows by KC rows of B
-            // per stage, so visiting again before the window has grown finds work only when rows are dense (busy) or when the
-            // window cannot grow (full ring / last chunk: drain it, taking partial batches -- "forced").
-            if (have < nchunks && have - rel < (uint32_t)TS) {
-                uint64_t *bar = t_full + have % TS;
-                const uint32_t par = (have / TS) & 1;
-                bool got = true;
-                if (busy) got = __shfl_sync(0xFFFFFFFFu, mbar_test(bar, par) ? 1 : 0, 0) != 0;
-                else mbar_wait(bar, par);
-                if (got) {
-                    ++have;
-                    tc_fence_after();
-                }
-            }
-            const uint32_t wend = have * KC;
-            const bool forced = (have - rel == (uint32_t)TS) || (have == nchunks);     // the window cannot grow: take what fits
-            const uint32_t bi = __ballot_sync(0xFFFFFFFFu, ecol < wend);               // entry inside the window (kPad never is)
-            const uint32_t bv = __ballot_sync(0xFFFFFFFFu, ecol != kPad);              // entry exists
-            // one bit per row (bit 4 i): fm = all four look-ahead entries inside the window (straight-line batch);
-            // pm = some inside and either the row ends with them or the window cannot grow (exact-count path)
-            const uint32_t fm = bi & (bi >> 1) & (bi >> 2) & (bi >> 3) & 0x11111111u;
-            const uint32_t nz = (bi | (bi >> 1) | (bi >> 2) | (bi >> 3)) & 0x11111111u;
-            const uint32_t dx = bi ^ bv;
-            const uint32_t ne = (dx | (dx >> 1) | (dx >> 2) | (dx >> 3)) & 0x11111111u;  // some existing entry is outside
-            const uint32_t pm = nz & ~fm & (forced ? 0xFFFFFFFFu : ~ne);
-            const uint32_t work = fm | pm;
-            busy = __popc(fm) >= 6;
-            if (work) {
-                sc[lane] = make_uint2(tq + ((ecol & 127u) << 2), __float_as_uint(eval));
-                __syncwarp();
-                // this lane's row: how far it advances; its next look-ahead is loaded now, behind this visit's entries
-                {
-                    const uint32_t sh = lane & 28u;
-                    const uint32_t adv = ((fm >> sh) & 1u) ? 4u : (((pm >> sh) & 1u) ? (uint32_t)__popc((bi >> sh) & 0xFu) : 0u);
-                    if (adv) {
-                        cur += adv * STEP;
-                        fetch();
-                    }
-                }
+        uint32_t ch = 0;
+        bool fresh = true;
+        while (ch < nchunks) {
+            const uint32_t k1 = (ch + 1) * KC;
+            // entries of the look-ahead inside this chunk: a prefix of every row's 8 lanes (ascending columns)
+            uint32_t m[NS];
+            bool more = false;
 #pragma unroll
-                for (int i = 0; i < RW; ++i) {
-                    if ((work >> (4 * i)) & 1u) {                                      // warp-uniform
-                        const uint32_t sp = sc_sa + i * (L * 8);
-                        if ((fm >> (4 * i)) & 1u) row_batch<4>(acc[i], sp);
-                        else row_entries<4>(acc[i], sp, (uint32_t)__popc((bi >> (4 * i)) & 0xFu));
+            for (int s = 0; s < NS; ++s) {
+                m[s] = __ballot_sync(0xFFFFFFFFu, ecol[s] < k1);
+                sc[s * 32 + lane] = make_uint2(tq + ((ecol[s] & 127u) << 2), __float_as_uint(eval[s]));
+#pragma unroll
+                for (int b = 0; b < 4; ++b) more |= ((m[s] >> (8 * b)) & 0xFFu) == 0xFFu;     // all 8 inside: maybe more behind them
+            }
+            __syncwarp();
+            // advance and issue the loads of the next visit now: their latency hides behind this visit's entries
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                cur[s] += (uint32_t)__popc((m[s] >> (lane & 24u)) & 0xFFu) * STEP;
+                fetch(s);
+            }
+            if (fresh) {
+                mbar_wait(t_full + ch % TS, (ch / TS) & 1);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int i = 0; i < RW; ++i) {
+                const uint32_t n = (uint32_t)__popc((m[i >> 2] >> (8 * (i & 3))) & 0xFFu);     // warp-uniform
+                const uint32_t sp = sc_sa + i * (L * 8);
+                if (n > 0) {
+                    row_entries<HB>(acc[i], sp, n);
+                    if (n > HB) {
+                        row_entries<HB>(acc[i], sp + HB * 8, n - HB);
+                        if (HB == 2 && n > 4) {
+                            row_entries<HB>(acc[i], sp + 32, n - 4);
+                            if (n > 6) row_entries<HB>(acc[i], sp + 48, n - 6);
+                        }
                     }
                 }
-                __syncwarp();                          // every lane is done with the scratch before the next visit overwrites it
+            }
+            __syncwarp();                              // every lane is done with the scratch before the next visit overwrites it
+            if (!more) {
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(t_empty + ch % TS);
+                ++ch;
+                fresh = true;
+            } else {
+                fresh = false;
             }
         }
 
@@ -413,13 +413,15 @@ int spmm_rows_quad(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float
     if (N % tmemk::kNT != 0)
         return set_error(CUSPMM_ERR_UNSUPPORTED, "the all-TMEM kernel needs N %% 512 == 0 (N=%u)", N);
     (void)nnz;
-    // tuning hook: CUSPMM_QUAD_SHAPE = <groups><issuers>, e.g. 71 (default), 72, 61, 62
-    static const int shape = getenv("CUSPMM_QUAD_SHAPE") ? atoi(getenv("CUSPMM_QUAD_SHAPE")) : 71;
+    // tuning hook: CUSPMM_QUAD_SHAPE = <groups><issuers><loads per wait>, e.g. 714 (default), 724, 712, 624
+    static const int shape = getenv("CUSPMM_QUAD_SHAPE") ? atoi(getenv("CUSPMM_QUAD_SHAPE")) : 714;
     switch (shape) {
-    case 72: return quadk::launch_quad<quadk::QuadCfg<7, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    case 61: return quadk::launch_quad<quadk::QuadCfg<6, 1>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    case 62: return quadk::launch_quad<quadk::QuadCfg<6, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
-    default: return quadk::launch_quad<quadk::QuadCfg<7, 1>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    case 724: return quadk::launch_quad<quadk::QuadCfg<7, 2, 4>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    case 712: return quadk::launch_quad<quadk::QuadCfg<7, 1, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    case 722: return quadk::launch_quad<quadk::QuadCfg<7, 2, 2>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    case 624: return quadk::launch_quad<quadk::QuadCfg<6, 2, 4>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    case 614: return quadk::launch_quad<quadk::QuadCfg<6, 1, 4>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+    default: return quadk::launch_quad<quadk::QuadCfg<7, 1, 4>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
     }
 }
 template int spmm_rows_quad<false>(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, uint64_t,

@@ -289,6 +289,16 @@ int cuspmm_cusparse_spmm_bsr(const uint32_t *blockRowPtrs_dev, const uint32_t *b
                              const float *B_dev, uint32_t N, float *C_dev, int warmup, int iters,
                              float *avg_ms, float *min_ms);
 
+/* cuSPARSE Blocked-ELL SpMM (fp32, CUSPARSE_SPMM_BLOCKED_ELL_ALG1): the ELL descriptor the reference leaves unimplemented
+ * (src/formats/sparse_ell.cu:92-105 throws "not implemented").  Blocked-ELL is cuSPARSE's only ELL
+ * flavour: every block row holds the same number of bs x bs blocks, so the BSR operand given here is padded on the device to
+ * its longest block row (column index -1, zero values); that re-layout is outside the timed region.  *ell_width_blocks
+ * (optional) receives the padded width in blocks. */
+int cuspmm_cusparse_spmm_blockedell(const uint32_t *blockRowPtrs_dev, const uint32_t *blockColIdxs_dev, const float *blocks_dev,
+                                    uint32_t numBlockRows, uint32_t numBlockCols, uint32_t numBlocks, uint32_t blockSize,
+                                    const float *B_dev, uint32_t N, float *C_dev, int warmup, int iters,
+                                    float *avg_ms, float *min_ms, uint32_t *ell_width_blocks);
+
 #ifdef __cplusplus
 }
 #endif

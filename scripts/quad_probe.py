@@ -39,7 +39,7 @@ def timed(fn, iters=5, warmup=2):
 
 
 def check():
-    shape = os.environ.get("CUSPMM_QUAD_SHAPE", "71")
+    shape = os.environ.get("CUSPMM_QUAD_SHAPE", "714")
     bad = 0
     cases = []
     for M in (1, 7, 8, 9, 55, 56, 57, 300, 1000, 4096):
@@ -87,7 +87,7 @@ def check():
 
 
 def time_variants(names):
-    shape = os.environ.get("CUSPMM_QUAD_SHAPE", "71")
+    shape = os.environ.get("CUSPMM_QUAD_SHAPE", "714")
     for name in names:
         if name.startswith("panel"):                       # a 1/8 row panel of large_25605 (strong-scaling shape)
             M, K, d, N = 25605 // int(name[5:]), 25605, 0.10, 512

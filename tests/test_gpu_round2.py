@@ -307,3 +307,20 @@ def test_cfg4_bsr_tcgen05_full_size(b, wl, bs, dtype):
     Br = Bd.to(tdt).to(torch.float64)
     expect, scale = w @ Br, wa @ Br.abs() + 1e-30
     assert ((C.to(torch.float64).sum(dim=0) - expect).abs() / scale).max().item() < 1e-6
+
+
+def test_cusparse_blocked_ell_baseline_agrees_with_oracle(b):
+    """the Blocked-ELL vendor baseline (the reference's ELL descriptor throws) -- and, like every
+    baseline here, its result is checked."""
+    import torch
+    a = random_csr(1024, 768, 0.03, seed=81)
+    bsr = orc.csr_to_bsr(a, 16, 16)
+    N = 128
+    B = np.random.default_rng(82).uniform(-1, 1, (bsr.K, N)).astype(np.float32)
+    out = torch.zeros((bsr.M, N), device="cuda")
+    avg, mn, w = b.cusparse_spmm_blockedell(b.dev_u32(bsr.blockRowPtrs), b.dev_u32(bsr.blockColIdxs), b.dev_f32(bsr.blocks),
+                                            bsr.M // 16, bsr.K // 16, 16, b.dev_f32(B), out, warmup=1, iters=2)
+    assert avg > 0 and mn > 0
+    assert w == int(np.diff(bsr.blockRowPtrs.astype(np.int64)).max())
+    den = orc.absprod_csr(orc.csr_from_dense(orc.to_dense(bsr)), B)
+    assert orc.max_rel_err(out.cpu().numpy(), orc.spmm_bsr(bsr, B), den) <= 1e-4
