@@ -624,17 +624,17 @@ def main():
             api = "cuspmm_spmm_csr_host (pinned host CSR + B in, C out; wall clock around the call)"
             h2d = 4 * (M + 1) + 8 * nnz_total + 4 * K * N
         else:
-            ks = (K + world - 1) // world                    # B rows per rank (padded so that the slices are equal)
+            ks = sh.b_slice_rows(K, world)                  # B rows per rank (padded so that the slices are equal)
             B_full = torch.zeros((ks * world, N), dtype=torch.float32, device="cuda")
             B_slice = torch.empty((ks, N), dtype=torch.float32, device="cuda")
             Bs_h = torch.zeros((ks, N), dtype=torch.float32).pin_memory()
-            k0, k1 = rank * ks, min(K, (rank + 1) * ks)
+            k0, k1 = sh.local_b_slice(None, K, rank, world)
             if k1 > k0:
                 Bs_h[:k1 - k0] = Bd[k0:k1].cpu()
 
             def e2e_step():
                 B_slice.copy_(Bs_h, non_blocking=True)                      # this rank's slice of B over its own PCIe link
-                dist.all_gather_into_tensor(B_full, B_slice)                # completed over NVLink
+                sh.allgather_B(B_full, B_slice)                             # completed over NVLink
                 return b.spmm_csr_host_devB(rp_h, ci_h, va_h, Ml, K, B_full[:K], C_h, variant=args.variant)
             api = ("per rank: H2D of its A panel + its 1/N slice of B, NCCL all_gather of B over NVLink, "
                    "cuspmm_spmm_csr_host_devB, D2H of its C rows; wall clock, max over ranks")

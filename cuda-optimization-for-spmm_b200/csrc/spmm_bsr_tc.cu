@@ -26,6 +26,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace cuspmm_b200 {
 namespace bsrtc {
@@ -219,6 +220,203 @@ bsr_tc_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *__restr
     }
 }
 
+// ==================================================================================== panel kernel (union walk)
+// The block-row kernel above drags a bs x 512 slab of B through L2 -> SM for EVERY stored block (32 flop per byte at 32x32;
+// ncu r01: L2 -> SM 12-16 TB/s, tensor pipe 17-20 %).  This kernel gives a CTA a PANEL of P consecutive block rows x 128 columns
+// of C (one UMMA M-tile) and walks the UNION of the panel's block columns in ascending order: the slab of B belonging to block
+// column j is fetched ONCE and multiplied against every block row of the panel that stores a block in column j.  At 10 %
+// block density a panel of 11 block rows touches 69 % of the block columns for 1.1 blocks per column: 0.62 slabs per block
+// instead of 1 (P = 16: 0.51).  Accumulators: D_p = TMEM columns [p * bs, (p + 1) * bs), P * bs <= 512.
+//   warp 0  producer: P cursors (lane = block row), REDUX.min = next block column of the union, ballot = the rows that hit
+//           it; per stage: the 128-column slab of that block column (bs/8 bulk copies of 2 KB) + up to kHitsPerStage blocks;
+//           the hit mask travels in shared memory beside the stage
+//   warp 1  MMA issuer: for every hit row p: D_p += slab^T x block^T (bs/16 x tcgen05.mma M128 N=bs K16); commit frees the stage
+//   warps 2..5 epilogue: tcgen05.ld.x16 per block row -> 128-byte row stores
+// Grid = (ceil(numBlockRows / P), Npad / 128); the host picks P so that the grid is just under a whole number of waves.
+constexpr int kHitsPerStage = 4;
+template <int BS>
+struct PanelSmem {
+    static constexpr int kStages = BS == 16 ? 20 : 12;
+    static constexpr uint32_t kBlockBytes = BS * BS * 2;
+    static constexpr uint32_t kSlabBytes = BS * 128 * 2;                     // bs k-rows x 128 n x 16 bit
+    static constexpr uint32_t kStageBytes = kSlabBytes + kHitsPerStage * kBlockBytes;
+    // the panel's block column indices, staged once: the union walk is a serial chain (min over the cursors -> hit mask ->
+    // advance -> next index), and with the indices in global memory every step paid an L2 round trip (first version: 0.68 ms
+    // against 0.18 ms for the block-row kernel); indices beyond the buffer (very dense panels) are still read from global memory
+    static constexpr uint32_t kIdxCap = 6144;
+    static constexpr uint32_t kTotal = kStages * kStageBytes + (2 * kStages + 1) * 8 + kStages * 4 + kIdxCap * 4 + 16 + 128;
+    static_assert(kTotal <= 232448, "more than 227 KB of shared memory");
+};
+
+template <int BS, int FMT>
+__global__ void __launch_bounds__(kThreads)
+bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *__restrict__ blockColIdxs,
+                    const uint16_t *__restrict__ blocksQ,   // [numBlocks][BS/8][BS][8]
+                    const uint16_t *__restrict__ Bq,        // [Kpad/8][Npad][8]
+                    uint32_t numBlockRows, uint32_t P, uint32_t tmemCols, uint32_t Npad, uint32_t N,
+                    float *__restrict__ C, size_t ldc) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using S = PanelSmem<BS>;
+    constexpr int kStages = S::kStages;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * S::kStageBytes);
+    uint64_t *empty = full + kStages;
+    uint64_t *accum_full = empty + kStages;
+    uint32_t *meta = reinterpret_cast<uint32_t *>(accum_full + 1);          // hit mask of each stage (0 = end of the walk)
+    uint32_t *idx_s = meta + kStages;                                       // blockColIdxs[base .. base + kIdxCap)
+    uint32_t *tmem_slot = idx_s + S::kIdxCap;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t R0 = blockIdx.x * P;
+    const uint32_t n0 = blockIdx.y * 128;
+    const uint32_t idxBase = __ldg(blockRowPtrs + R0);
+    {
+        const uint32_t idxEnd = __ldg(blockRowPtrs + min(R0 + P, numBlockRows));
+        const uint32_t cnt = min(idxEnd - idxBase, S::kIdxCap);
+        for (uint32_t t = threadIdx.x; t < cnt; t += kThreads) idx_s[t] = __ldg(blockColIdxs + idxBase + t);
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(accum_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer: union walk over the panel's block columns
+        uint32_t cur = 0, end = 0;
+        if (lane < P && R0 + lane < numBlockRows) {
+            cur = __ldg(blockRowPtrs + R0 + lane);
+            end = __ldg(blockRowPtrs + R0 + lane + 1);
+        }
+        auto col_at = [&](uint32_t c) -> uint32_t {
+            if (c >= end) return 0xFFFFFFFFu;
+            const uint32_t o = c - idxBase;
+            return o < S::kIdxCap ? idx_s[o] : __ldg(blockColIdxs + c);
+        };
+        uint32_t col = col_at(cur);
+        uint32_t i = 0;
+        while (true) {
+            const uint32_t j = __reduce_min_sync(0xFFFFFFFFu, col);
+            if (j == 0xFFFFFFFFu) break;
+            uint32_t hit = __ballot_sync(0xFFFFFFFFu, col == j);
+            while (hit) {
+                uint32_t take = 0, h = hit;
+#pragma unroll
+                for (int k = 0; k < kHitsPerStage; ++k) { take |= h & (0u - h); h &= h - 1u; }
+                const uint32_t s = i % kStages, it = i / kStages;
+                if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+                unsigned char *slab = smem + s * S::kStageBytes;
+                unsigned char *blk = slab + S::kSlabBytes;
+                if (lane == 0) {
+                    meta[s] = take;
+                    mbar_expect_tx(full + s, S::kSlabBytes + (uint32_t)__popc(take) * S::kBlockBytes);
+                }
+                __syncwarp();
+                // the copies of a stage are issued by different lanes: lanes 31, 30, .. the bs/8 pieces of the slab (the panel has
+                // at most 32 - bs/8 block rows when those lanes are rows too -- they then issue both), hit rows their block
+                if (lane >= 32u - BS / 8) {
+                    const uint32_t kb = 31u - lane;
+                    const uint16_t *src = Bq + ((size_t)j * (BS / 8) * Npad + n0) * 8;
+                    bulk_g2s(slab + (size_t)kb * 128 * 16, src + (size_t)kb * Npad * 8, 128 * 16, full + s);
+                }
+                if ((take >> lane) & 1u) {
+                    const uint32_t slot = (uint32_t)__popc(take & ((1u << lane) - 1u));
+                    bulk_g2s(blk + slot * S::kBlockBytes, blocksQ + (size_t)cur * BS * BS, S::kBlockBytes, full + s);
+                }
+                hit &= ~take;
+                ++i;
+            }
+            if (col == j) {
+                ++cur;
+                col = col_at(cur);
+            }
+        }
+        // end marker: a stage with an empty hit mask and no bytes
+        {
+            const uint32_t s = i % kStages, it = i / kStages;
+            if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+            if (lane == 0) {
+                meta[s] = 0u;
+                pipe::mbar_arrive(full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(FMT, 128, BS);
+            uint32_t touched = 0;
+            for (uint32_t i = 0;; ++i) {
+                const uint32_t s = i % kStages, it = i / kStages;
+                mbar_wait(full + s, it & 1);
+                uint32_t m = meta[s];
+                if (m == 0u) break;
+                tc_fence_after();
+                const uint32_t slab = smem_u32(smem + s * S::kStageBytes);
+                uint32_t blk = slab + S::kSlabBytes;
+                while (m) {
+                    const uint32_t p = (uint32_t)__ffs((int)m) - 1u;
+                    m &= m - 1u;
+#pragma unroll
+                    for (int ks = 0; ks < BS / 16; ++ks) {
+                        const uint64_t bdesc = make_desc(blk + ks * 2 * BS * 16, BS * 16, 128);       // block k-groups 2ks, 2ks+1
+                        const uint64_t adesc = make_desc(slab + ks * 2 * 128 * 16, 128 * 16, 128);    // slab k-groups 2ks, 2ks+1
+                        umma_f16(tmem_base + p * BS, adesc, bdesc, idesc, (((touched >> p) & 1u) | (uint32_t)ks) ? 1u : 0u);
+                    }
+                    touched |= 1u << p;
+                    blk += S::kBlockBytes;
+                }
+                umma_commit(empty + s);          // stage s may be refilled once these MMAs have read it
+            }
+            umma_commit(accum_full);             // all accumulators final
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const uint32_t q = warp & 3;             // TMEM lane quarter this warp may access
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const uint32_t n = n0 + q * 32 + lane;
+        for (uint32_t p = 0; p < P && R0 + p < numBlockRows; ++p) {
+            const uint32_t R = R0 + p;
+            const bool has = __ldg(blockRowPtrs + R + 1) > __ldg(blockRowPtrs + R);      // a block row without blocks is a zero row of C
+#pragma unroll
+            for (int half = 0; half < BS / 16; ++half) {
+                uint32_t v[16];
+                if (has) {
+                    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + p * BS + half * 16;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+                                 "tcgen05.wait::ld.sync.aligned;"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(taddr) : "memory");
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) v[jj] = 0u;
+                }
+                if (n < N) {
+                    float *cp = C + ((size_t)R * BS + half * 16) * ldc + n;
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) __stcs(cp + (size_t)jj * ldc, __uint_as_float(v[jj]));   // 32 lanes = one 128-byte line
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ operand preparation
 template <typename T> __device__ __forceinline__ uint16_t cvt16(float x);
 template <> __device__ __forceinline__ uint16_t cvt16<__nv_bfloat16>(float x) { return __bfloat16_as_ushort(__float2bfloat16_rn(x)); }
@@ -326,6 +524,35 @@ extern "C" int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan p, const float *B, uint32
 
 template <int BS, int FMT>
 static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
+    // panel kernel (union walk) whenever there are enough block rows for panels of >= 2; the block-row kernel otherwise.
+    // Tuning hooks: CUSPMM_BSR_PANEL = 0 / 1 forces the choice, CUSPMM_BSR_P the panel height.
+    static const int forcePanel = getenv("CUSPMM_BSR_PANEL") ? atoi(getenv("CUSPMM_BSR_PANEL")) : -1;
+    static const int forceP = getenv("CUSPMM_BSR_P") ? atoi(getenv("CUSPMM_BSR_P")) : 0;
+    const uint32_t ytiles = p->Npad / 128;
+    const uint32_t sms = (uint32_t)sm_count();
+    constexpr uint32_t Pmax = 512 / BS > 32 ? 32 : 512 / BS;
+    uint32_t P = 1;
+    for (uint32_t w = 1; w <= 64; ++w) {                 // the smallest whole number of waves whose panels fit into TMEM
+        const uint32_t want = (w * sms) / ytiles;
+        if (want == 0) continue;
+        P = (p->numBlockRows + want - 1) / want;
+        if (P <= Pmax) break;
+        P = Pmax;
+    }
+    if (forceP > 0) P = (uint32_t)forceP > Pmax ? Pmax : (uint32_t)forceP;
+    if (P < 1) P = 1;
+    const bool usePanel = forcePanel >= 0 ? forcePanel != 0 : P >= 2;
+    if (usePanel) {
+        auto kern = bsrtc::bsr_tc_panel_kernel<BS, FMT>;
+        CUSPMM_CUDA(set_smem_once(kern, bsrtc::PanelSmem<BS>::kTotal));
+        uint32_t cols = 32;
+        while (cols < P * BS) cols <<= 1;
+        dim3 grid((p->numBlockRows + P - 1) / P, ytiles);
+        kern<<<grid, bsrtc::kThreads, bsrtc::PanelSmem<BS>::kTotal, st>>>(p->blockRowPtrs, p->blockColIdxs, p->blocksQ, p->Bq,
+                                                                           p->numBlockRows, P, cols, p->Npad, p->N, C, ldc);
+        CUSPMM_LAUNCH_CHECK("bsr_tc_panel_kernel");
+        return CUSPMM_OK;
+    }
     auto kern = bsrtc::bsr_tc_kernel<BS, FMT>;
     CUSPMM_CUDA(set_smem_once(kern, bsrtc::Smem<BS>::kTotal));
     dim3 grid(p->numBlockRows, (p->Npad + bsrtc::kMaxTileN - 1) / bsrtc::kMaxTileN);

@@ -239,7 +239,33 @@ struct Cfg {
 // SELL = false: CSR (rowPtrs = row pointers, entry idx of a row at colIdxs[idx], idx absolute).
 // SELL = true : sliced ELL (rowPtrs = slicePtrs; entry j of row r at slicePtrs[r/32] + j*32 + r%32,
 //               j in [0, W_slice); padding entries carry colIdx kPad and are never consumed).
-template <class CFG, bool SELL>
+// ---- thread-block-cluster helpers (CS > 1: the CTAs of a cluster share every B chunk through multicast TMA)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(pipe::smem_u32(bar)), "r"(rank) : "memory");
+}
+// 1-D TMA bulk copy global -> the same shared-memory offset of every CTA in ctaMask; each destination's mbarrier gets the bytes
+__device__ __forceinline__ void bulk_g2s_multicast(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t ctaMask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(pipe::smem_u32(dst)), "l"(src), "r"(bytes), "r"(pipe::smem_u32(bar)), "h"(ctaMask) : "memory");
+}
+
+// CS = CTAs per cluster (1: no cluster).  CS > 1 (column tile == all of B's columns only): the CS CTAs of a cluster own
+// consecutive row panels and walk the same chunks of B; every CTA fetches 1/CS of a chunk and multicasts it into all of them,
+// so a chunk crosses the L2 -> SM fabric once per cluster instead of once per CTA (short row panels -- the 1/8 panel of a
+// strong-scaled matrix -- are bound by exactly that traffic: 148 CTAs x 52 MB in 0.63 ms = 12 TB/s).  A ring stage is
+// refilled when the consumers of ALL CTAs of the cluster have released it (arrives on every CTA's `empty` barrier).
+template <class CFG, bool SELL, int CS = 1>
 __global__ void __launch_bounds__(CFG::kThreads, 1)
 csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs,
                   const float *__restrict__ vals, uint32_t M, uint32_t K, uint32_t rpc,
@@ -266,17 +292,50 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
     // consumer warps that got no rows (the last panel, or rpc < the CTA's row slots) leave at once: spinning on the
     // barriers they would steal issue slots from the working warps (4096^2: 14 of 31 warps have rows)
     const uint32_t activeWarps = rowEnd > row0 ? min((uint32_t)NW, (rowEnd - row0 + RW - 1) / RW) : 0u;
+    uint32_t crank = 0, clusterWarps = activeWarps;          // consumer warps of the whole cluster (arrivals per `empty` phase)
+    if constexpr (CS > 1) {
+        crank = cluster_ctarank();
+        clusterWarps = 0;
+        const uint32_t firstPanel = blockIdx.x - crank;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) {
+            const uint32_t a0 = (firstPanel + r) * rpc, a1 = min(M, a0 + rpc);
+            clusterWarps += a1 > a0 ? min((uint32_t)NW, (a1 - a0 + RW - 1) / RW) : 0u;
+        }
+    }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, max(activeWarps, 1u)); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, max(clusterWarps, 1u)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (activeWarps == 0 || (warp < NW && warp >= activeWarps)) return;
+    if constexpr (CS > 1) {
+        cluster_sync_all();                                  // every CTA's barriers exist before anybody multicasts / arrives remotely
+    } else {
+        if (activeWarps == 0 || (warp < NW && warp >= activeWarps)) return;
+    }
+    const bool clusterIdle = CS > 1 && clusterWarps == 0;    // no rows in the whole cluster: nothing to stream
 
     if (warp == NW) {
         // ------------------------------------------------------------ producer
         // lane 0 arms the barrier; when the tile rows are not contiguous in B (NT < ldb) all 32
         // lanes issue row copies in parallel (one thread issuing KC copies would be the bottleneck)
+        if constexpr (CS > 1) {
+            // cluster: this CTA fetches rows [crank * KC / CS, (crank + 1) * KC / CS) of every chunk and multicasts them
+            constexpr uint32_t kSlice = KC / CS;
+            for (uint32_t ch = 0; ch < nchunks && !clusterIdle; ++ch) {
+                const uint32_t s = ch % STAGES, it = ch / STAGES;
+                if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+                const uint32_t k0 = ch * KC;
+                const uint32_t rows = min((uint32_t)KC, K - k0);
+                if (lane == 0) {
+                    mbar_expect_tx(full + s, rows * NT * (uint32_t)sizeof(float));          // the whole chunk lands here
+                    const uint32_t lo = crank * kSlice, hi = min(rows, lo + kSlice);
+                    if (hi > lo)
+                        bulk_g2s_multicast(tiles + (size_t)s * KC * NT + (size_t)lo * NT, B + (size_t)(k0 + lo) * ldb + col0,
+                                           (hi - lo) * NT * (uint32_t)sizeof(float), full + s, (uint16_t)((1u << CS) - 1u));
+                }
+            }
+        } else
         for (uint32_t ch = 0; ch < nchunks; ++ch) {
             const uint32_t s = ch % STAGES, it = ch / STAGES;
             if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
@@ -294,7 +353,14 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
                              NT * (uint32_t)sizeof(float), full + s);
             }
         }
+        if constexpr (CS > 1) cluster_sync_all();            // nobody leaves while a peer may still write here
         return;
+    }
+    if constexpr (CS > 1) {
+        if (warp >= activeWarps) {                           // consumer warp without rows: only the final cluster barrier
+            cluster_sync_all();
+            return;
+        }
     }
 
     // ---------------------------------------------------------------- consumers
@@ -388,7 +454,11 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
+        if constexpr (CS > 1) {
+            if (lane < (uint32_t)CS) mbar_arrive_remote(empty + s, lane);      // lane r releases the stage in CTA r of the cluster
+        } else {
+            if (lane == 0) mbar_arrive(empty + s);
+        }
     }
 
 #pragma unroll
@@ -400,6 +470,7 @@ csr_staged_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restri
             for (int u = 0; u < U; ++u) __stcs(crow + u * 32, acc[i][u]);
         }
     }
+    if constexpr (CS > 1) cluster_sync_all();
 }
 
 // whole waves: (row panels x column tiles) is made a multiple of the SM count, rows per CTA =
@@ -432,6 +503,30 @@ int launch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, 
     return CUSPMM_OK;
 }
 
+// the staged kernel in clusters of CS CTAs (column tile == all N columns of B, ldb == NT)
+template <class CFG, bool SELL, int CS>
+int launch_cluster(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K,
+                   const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+    auto kern = csr_staged_kernel<CFG, SELL, CS>;
+    CUSPMM_CUDA(set_smem_once(kern, CFG::kSmemBytes));
+    const GridPlan g = plan_grid(M, 1, CFG::kRows);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((g.panels + CS - 1) / CS * CS, 1, 1);
+    cfg.blockDim = dim3(CFG::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = CFG::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUSPMM_CUDA(cudaLaunchKernelEx(&cfg, kern, rowPtrs, colIdxs, vals, M, K, g.rpc, B, N, ldb, C, ldc));
+    CUSPMM_LAUNCH_CHECK("csr_staged_kernel (cluster)");
+    return CUSPMM_OK;
+}
+
 template <bool SELL>
 int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                 const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
@@ -452,6 +547,22 @@ int launch_by_N(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
         // (sliced ELL keeps 15 x 4: its window refills are strided 128-byte-apart loads, and 16 warps sharing a
         //  slice through a 30 KB L1 measured 6 % slower than 8 warps: 5.24 vs 4.92 ms on large_25605)
         if (shape == 0) shape = plan_grid(M, ytiles, 62).rpc >= 30 ? (SELL ? 4 : 31) : (SELL ? 2 : 1);
+        // clusters with multicast TMA: tuning hook CUSPMM_STAGED_CLUSTER = 2 / 4, never selected.  Measured (bit-identical;
+        // profiles/r02_cluster_multicast_probe.jsonl): the 1/8 row panel of large_25605 0.62 ms without, 0.92 / 1.84 / 1.95 ms in
+        // clusters of 2 / 4 / 8, the full matrix 4.34 -> 4.91 / 6.62 ms: the release of a ring stage now needs a round trip
+        // through every CTA of the cluster and a 3-deep ring cannot hide it, and nothing is gained on the other side because
+        // short panels are bound by the WRITES of the B chunks into shared memory (410 K of 1.3 M wavefronts per CTA), which
+        // multicast does not reduce -- not by L2 -> SM bandwidth.
+        static const int forceCS = getenv("CUSPMM_STAGED_CLUSTER") ? atoi(getenv("CUSPMM_STAGED_CLUSTER")) : 0;
+        if (N == 512 && ldb == 512 && forceCS > 1) {
+            if (shape == 1) {
+                if (forceCS == 2) return launch_cluster<Cfg<512, 31, 1, 32, 3>, SELL, 2>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+                if (forceCS == 4) return launch_cluster<Cfg<512, 31, 1, 32, 3>, SELL, 4>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+            } else if (shape == 31) {
+                if (forceCS == 2) return launch_cluster<Cfg<512, 31, 2, 32, 3>, SELL, 2>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+                if (forceCS == 4) return launch_cluster<Cfg<512, 31, 2, 32, 3>, SELL, 4>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
+            }
+        }
         if (shape == 1) return launch<Cfg<512, 31, 1, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         if (shape == 31) return launch<Cfg<512, 31, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);
         if (shape == 2) return launch<Cfg<512, 15, 2, 32, 3>, SELL>(rowPtrs, colIdxs, vals, M, K, B, N, ldb, C, ldc, st);

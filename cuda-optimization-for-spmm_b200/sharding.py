@@ -2,7 +2,8 @@
 how per-rank timings / work are combined, and how unequal C panels are gathered.
 
 Rows of C are independent (reference: src/spmm/csr/spmm_csr.cpp:15-27), so there is NO collective in
-the data path; the only collectives are the timing reductions and the optional gather of C.
+the device-timed data path; the collectives are the timing reductions, the optional gather of C and -- in the end-to-end
+(host operands) path -- the all-gather that completes B from the 1/world row slices every rank uploads over its own PCIe link.
 Backend-agnostic (nccl on GPUs, gloo in the CPU tests)."""
 from __future__ import annotations
 
@@ -64,3 +65,24 @@ def gather_panels(C_local: torch.Tensor, splits) -> torch.Tensor:
     bufs = [torch.empty_like(pad) for _ in range(W)]
     dist.all_gather(bufs, pad)
     return torch.cat([bufs[g][:heights[g]] for g in range(W)], dim=0)
+
+
+def b_slice_rows(K: int, world_size: int) -> int:
+    """Rows of B every rank uploads in the end-to-end path: equal slices (all_gather needs them equal), the last one padded."""
+    return (K + world_size - 1) // world_size
+
+
+def local_b_slice(B_rows_of_rank, K: int, rank: int, world_size: int):
+    """(k0, k1): the rows of B that rank owns; rows past K are padding."""
+    ks = b_slice_rows(K, world_size)
+    return rank * ks, min(K, (rank + 1) * ks)
+
+
+def allgather_B(B_full: torch.Tensor, B_slice: torch.Tensor) -> torch.Tensor:
+    """B_full[(world * ks) x N] <- the ranks' slices [ks x N] in rank order (NCCL: over NVLink; gloo in the CPU tests).
+    Rows [0, K) of the result are B."""
+    if world() == 1:
+        B_full[:B_slice.shape[0]].copy_(B_slice)
+        return B_full
+    dist.all_gather_into_tensor(B_full, B_slice)
+    return B_full

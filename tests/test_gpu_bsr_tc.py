@@ -36,6 +36,11 @@ CASES = [
     (256, 256, 640, 32, 0.01),      # 512 + 128 columns
     (96, 96, 21, 16, 0.05),         # tiny N
     (160, 160, 128, 16, 0.0),       # no blocks at all: C must be zero
+    # enough block rows for the PANEL kernel (union walk over the block columns of P block rows; P from the grid fit)
+    (2048, 1024, 512, 16, 0.05),    # 128 block rows x 4 column tiles -> panels of 4
+    (3000, 700, 200, 32, 0.30),     # 94 block rows, N not a multiple of 128, most block columns hit by both rows of a panel
+    (11264, 256, 128, 16, 1.0),     # 704 block rows -> panels of 5, EVERY block column hit by all 5: more hits than a stage holds
+    (5000, 640, 384, 32, 0.002),    # sparse block rows, some empty, last panel ragged
 ]
 
 

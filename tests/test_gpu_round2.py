@@ -323,4 +323,5 @@ def test_cusparse_blocked_ell_baseline_agrees_with_oracle(b):
     assert avg > 0 and mn > 0
     assert w == int(np.diff(bsr.blockRowPtrs.astype(np.int64)).max())
     den = orc.absprod_csr(orc.csr_from_dense(orc.to_dense(bsr)), B)
-    assert orc.max_rel_err(out.cpu().numpy(), orc.spmm_bsr(bsr, B), den) <= 1e-4
+    # cuSPARSE runs fp32 Blocked-ELL on TF32 tensor cores (10-bit mantissa operands): observed 3.4e-4 component-wise
+    assert orc.max_rel_err(out.cpu().numpy(), orc.spmm_bsr(bsr, B), den) <= 2e-3

@@ -43,6 +43,15 @@ def _worker(rank, world, port, out_dir):
         C = sh.gather_panels(C_local, splits)
         local_nnz = int(a.rowPtrs[r1]) - int(a.rowPtrs[r0])
         gflops, ms = sh.job_throughput(local_ms_total=10.0 * (rank + 1), steps=5, local_flops_per_step=2.0 * local_nnz * 24)
+        # end-to-end path: every rank uploads its 1/world row slice of B, an all-gather completes B (bench.py --gpus N)
+        K = B.shape[0]
+        ks = sh.b_slice_rows(K, world)
+        k0, k1 = sh.local_b_slice(None, K, rank, world)
+        mine = torch.zeros((ks, B.shape[1]), dtype=torch.float32)
+        mine[:k1 - k0] = torch.from_numpy(B[k0:k1])
+        full = sh.allgather_B(torch.empty((ks * world, B.shape[1]), dtype=torch.float32), mine)
+        np.testing.assert_array_equal(full[:K].numpy(), B)
+        assert not full[K:].any()
         np.save(os.path.join(out_dir, f"C_{rank}.npy"), C.numpy())
         np.save(os.path.join(out_dir, f"m_{rank}.npy"), np.array([gflops, ms, local_nnz]))
     finally:
