@@ -524,8 +524,13 @@ extern "C" int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan p, const float *B, uint32
 
 template <int BS, int FMT>
 static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
-    // panel kernel (union walk) whenever there are enough block rows for panels of >= 2; the block-row kernel otherwise.
-    // Tuning hooks: CUSPMM_BSR_PANEL = 0 / 1 forces the choice, CUSPMM_BSR_P the panel height.
+    // The block-row kernel is the default.  The panel kernel (union walk) is correct (tests/test_gpu_bsr_tc.py runs it through
+    // the hook) but slower as built: 0.60 ms (32x32, P = 11) / 1.41 ms (16x16, P = 22) against 0.18 / 0.28 ms on BASELINE
+    // configs[3] (profiles/r02_bsr_panel_probe.jsonl).  Its stages are many SMALL bulk copies (2 KB slab pieces of a 128-column
+    // tile, 0.5-2 KB blocks) and the TMA unit retires roughly one bulk copy per ~200 clk per SM whatever its size (ncu: L2 -> SM
+    // 1.7 TB/s, every pipe idle, the MMA issuer waiting for data), so the bytes saved by sharing slabs are lost several times
+    // over; the block-row kernel moves 34 KB per two copies.  Tuning hooks: CUSPMM_BSR_PANEL = 1 selects the panel kernel,
+    // CUSPMM_BSR_P its panel height.
     static const int forcePanel = getenv("CUSPMM_BSR_PANEL") ? atoi(getenv("CUSPMM_BSR_PANEL")) : -1;
     static const int forceP = getenv("CUSPMM_BSR_P") ? atoi(getenv("CUSPMM_BSR_P")) : 0;
     const uint32_t ytiles = p->Npad / 128;
@@ -541,7 +546,7 @@ static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
     }
     if (forceP > 0) P = (uint32_t)forceP > Pmax ? Pmax : (uint32_t)forceP;
     if (P < 1) P = 1;
-    const bool usePanel = forcePanel >= 0 ? forcePanel != 0 : P >= 2;
+    const bool usePanel = forcePanel > 0;
     if (usePanel) {
         auto kern = bsrtc::bsr_tc_panel_kernel<BS, FMT>;
         CUSPMM_CUDA(set_smem_once(kern, bsrtc::PanelSmem<BS>::kTotal));

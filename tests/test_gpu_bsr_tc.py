@@ -106,3 +106,17 @@ def test_bsr_tc_integer_data_is_exact(b):
     finally:
         plan.close()
     np.testing.assert_array_equal(got, orc.spmm_bsr(o, B))
+
+
+def test_panel_kernel_through_the_hook():
+    """The panel kernel (union walk over the block columns of P block rows) is not the default; CUSPMM_BSR_PANEL = 1 selects it
+    (read once per process), so the parity cases above are re-run in a child process with the hook set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("CUSPMM_BSR_PANEL"):
+        pytest.skip("already inside the child run")
+    env = dict(os.environ, CUSPMM_BSR_PANEL="1")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-q", "-x", "-k",
+                        "test_bsr_tensor_core or integer_data"], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
