@@ -2,11 +2,13 @@
 // (north_star (b)).  The reference has no conversion code in C++ (SparseMatrixBSR::fromDense
 // throws, src/formats/sparse_bsr.cu:259); offline it is utils/python_utils/convert_mtx.py
 // (scipy tocsr/tocoo/tocsc/tobsr).  Every converter here is checked bit for bit against the
-// numpy restatements in oracle/oracle.py.  Sorting uses cub::DeviceRadixSort (part of the
-// CUDA toolkit); everything else is hand-written.
+// numpy restatements in oracle/oracle.py.  CSR -> BSR is sort-free (a shared-memory bitmap per block row);
+// column-ELL -> CSR, and CSR -> BSR for matrices with more than 393 216 block columns, sort with cub::DeviceRadixSort
+// (part of the CUDA toolkit); everything else is hand-written.
 #include "common.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <stdlib.h>
 
 namespace cuspmm_b200 {
 
@@ -273,6 +275,87 @@ __global__ void bsr_scatter_kernel(const uint64_t *__restrict__ keys, const uint
     blocks[(size_t)b * br * bc + (size_t)(r % br) * bc + (c % bc)] = vals[src];
 }
 
+// ------------------------------------------------------------------ CSR -> BSR without a sort (per-block-row bitmap)
+// The entries of a block row are one contiguous range of the CSR arrays (br consecutive rows), so no global sort is
+// needed: a CTA per block row marks the block columns it meets in a shared-memory bitmap (nbc bits); the bitmap IS the
+// ascending blockColIdxs of that block row, and "number of set bits below bit cb" is the position of block cb inside it.
+//   count: blocks per block row = popcount of the bitmap
+//   fill : rebuild the bitmap, prefix-popcount its words, emit blockColIdxs, scatter every entry into its block
+// Reads colIdxs twice and vals once, writes the blocks once: HBM-bound streaming instead of two 64-bit-key radix sorts of
+// all non-zeros (the sort path stays for matrices whose bitmap would not fit into shared memory).
+constexpr uint32_t kBsrBitmapMaxWords = 12288;      // x2 arrays (bits + prefix) = 96 KB: nbc <= 393 216 block columns
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+bsr_bitmap_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
+                  uint32_t M, uint32_t br, uint32_t bc, uint32_t words, uint32_t *__restrict__ counts,
+                  const uint32_t *__restrict__ blockRowPtrs, uint32_t *__restrict__ blockColIdxs, float *__restrict__ blocks) {
+    extern __shared__ uint32_t bm[];                 // [words] bits, then (FILL) [words] exclusive prefix popcounts
+    __shared__ uint32_t red[8];
+    uint32_t *pre = bm + words;
+    const uint32_t R = blockIdx.x;
+    const uint32_t rBeg = R * br, rEnd = min(M, rBeg + br);
+    const uint32_t i0 = __ldg(rowPtrs + rBeg), i1 = __ldg(rowPtrs + rEnd);
+    for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) bm[w] = 0u;
+    __syncthreads();
+    for (uint32_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const uint32_t cb = __ldg(colIdxs + i) / bc;
+        atomicOr(bm + (cb >> 5), 1u << (cb & 31u));
+    }
+    __syncthreads();
+    // popcount of the bitmap, as exclusive prefix per word when filling: each thread owns a contiguous run of words
+    const uint32_t per = (words + blockDim.x - 1) / blockDim.x;
+    const uint32_t w0 = min(words, threadIdx.x * per), w1 = min(words, w0 + per);
+    uint32_t mine = 0;
+    for (uint32_t w = w0; w < w1; ++w) mine += (uint32_t)__popc(bm[w]);
+    uint32_t incl = mine;                            // inclusive scan over the 256 threads
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane_id() >= (uint32_t)d) incl += y;
+    }
+    if (lane_id() == 31) red[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t warpBase = 0, total = 0;
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) {
+        if (w < (threadIdx.x >> 5)) warpBase += red[w];
+        total += red[w];
+    }
+    if constexpr (!FILL) {
+        if (threadIdx.x == 0) counts[R] = total;
+        return;
+    } else {
+        uint32_t run = warpBase + incl - mine;
+        for (uint32_t w = w0; w < w1; ++w) {
+            pre[w] = run;
+            run += (uint32_t)__popc(bm[w]);
+        }
+        __syncthreads();
+        const uint32_t base = __ldg(blockRowPtrs + R);
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) {        // ascending block columns of this block row
+            uint32_t bits = bm[w], k = pre[w];
+            while (bits) {
+                const uint32_t bit = (uint32_t)__ffs((int)bits) - 1u;
+                bits &= bits - 1u;
+                blockColIdxs[base + k++] = w * 32u + bit;
+            }
+        }
+        for (uint32_t r = rBeg; r < rEnd; ++r) {                            // every entry into its block (blocks are pre-zeroed)
+            const uint32_t p0 = __ldg(rowPtrs + r), p1 = __ldg(rowPtrs + r + 1);
+            for (uint32_t i = p0 + threadIdx.x; i < p1; i += blockDim.x) {
+                const uint32_t c = __ldg(colIdxs + i), cb = c / bc;
+                const uint32_t blk = base + pre[cb >> 5] + (uint32_t)__popc(bm[cb >> 5] & ((1u << (cb & 31u)) - 1u));
+                blocks[(size_t)blk * br * bc + (size_t)(r - rBeg) * bc + (c - cb * bc)] = ld_stream(vals + i);
+            }
+        }
+    }
+}
+
+static bool bsr_bitmap_fits(uint32_t nbc) {
+    static const bool forceSort = getenv("CUSPMM_BSR_CONVERT_SORT") != nullptr;       // tuning hook: the radix-sort path
+    return !forceSort && (nbc + 31) / 32 <= kBsrBitmapMaxWords;
+}
+
 // ------------------------------------------------------------------ column-ELL -> CSR
 __global__ void iota_kernel(uint32_t *idx, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,7 +511,13 @@ extern "C" int cuspmm_csr_to_bsr_count(const uint32_t *rowPtrs, const uint32_t *
     AsyncBuf counts(st);
     CUSPMM_CUDA(counts.alloc((size_t)(nbr + 1) * 4));
     CUSPMM_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)(nbr + 1) * 4, st));
-    if (nnz) {
+    if (nnz && bsr_bitmap_fits(nbc)) {
+        const uint32_t words = (nbc + 31) / 32;
+        auto kern = bsr_bitmap_kernel<false>;
+        CUSPMM_CUDA(set_smem_once(kern, (size_t)words * 4));
+        kern<<<nbr, 256, (size_t)words * 4, st>>>(rowPtrs, colIdxs, nullptr, M, br, bc, words, counts.as<uint32_t>(), nullptr, nullptr, nullptr);
+        CUSPMM_LAUNCH_CHECK("bsr_bitmap_kernel<count>");
+    } else if (nnz) {
         AsyncBuf keys(st), idx(st), flags(st);
         int rc = sort_bsr_keys(rowPtrs, colIdxs, M, nnz, br, bc, nbr, nbc, keys, idx, st);
         if (rc) return rc;
@@ -452,6 +541,24 @@ extern "C" int cuspmm_csr_to_bsr_fill(const uint32_t *rowPtrs, const uint32_t *c
     const uint32_t nbr = (M + br - 1) / br, nbc = (K + bc - 1) / bc;
     if (numBlocks) CUSPMM_CUDA(cudaMemsetAsync(blocks, 0, (size_t)numBlocks * br * bc * sizeof(float), st));
     if (!nnz) return CUSPMM_OK;
+    if (bsr_bitmap_fits(nbc)) {
+        // block row pointers again (the caller keeps only numBlocks between the two calls): count + scan, then fill
+        const uint32_t words = (nbc + 31) / 32;
+        AsyncBuf counts(st), brp(st);
+        CUSPMM_CUDA(counts.alloc((size_t)(nbr + 1) * 4));
+        CUSPMM_CUDA(brp.alloc((size_t)(nbr + 1) * 4));
+        auto kc = bsr_bitmap_kernel<false>;
+        auto kf = bsr_bitmap_kernel<true>;
+        CUSPMM_CUDA(set_smem_once(kc, (size_t)words * 4));
+        CUSPMM_CUDA(set_smem_once(kf, (size_t)words * 8));
+        kc<<<nbr, 256, (size_t)words * 4, st>>>(rowPtrs, colIdxs, nullptr, M, br, bc, words, counts.as<uint32_t>(), nullptr, nullptr, nullptr);
+        CUSPMM_LAUNCH_CHECK("bsr_bitmap_kernel<count>");
+        scan_exclusive_1block<<<1, 1024, 0, st>>>(counts.as<uint32_t>(), brp.as<uint32_t>(), nbr, 1u);
+        CUSPMM_LAUNCH_CHECK("scan_exclusive_1block");
+        kf<<<nbr, 256, (size_t)words * 8, st>>>(rowPtrs, colIdxs, vals, M, br, bc, words, nullptr, brp.as<uint32_t>(), blockColIdxs, blocks);
+        CUSPMM_LAUNCH_CHECK("bsr_bitmap_kernel<fill>");
+        return CUSPMM_OK;
+    }
     AsyncBuf keys(st), idx(st), flags(st), blockOf(st), sums(st), offs(st);
     int rc = sort_bsr_keys(rowPtrs, colIdxs, M, nnz, br, bc, nbr, nbc, keys, idx, st);
     if (rc) return rc;

@@ -155,9 +155,10 @@ int cuspmm_spmm_bsr_f32(const uint32_t *blockRowPtrs_dev, const uint32_t *blockC
  * unimplemented, src/formats/sparse_bsr.cu:259; offline it is scipy tobsr).
  * M and K are zero-padded up to multiples of br / bc.  _count fills
  * blockRowPtrs_dev[ceil(M/br)+1] and returns numBlocks (synchronises); _fill writes
- * ascending blockColIdxs and zero-filled row-major fp32 blocks.  Both sort the
- * (blockRow, blockCol) keys of the non-zeros with a device radix sort; temporaries
- * come from the stream-ordered allocator. */
+ * ascending blockColIdxs and zero-filled row-major fp32 blocks.  No sort: a CTA per block row marks the block columns of
+ * its (contiguous) CSR range in a shared-memory bitmap, whose prefix popcount is every block's position; matrices with more
+ * than 393 216 block columns fall back to a device radix sort of (blockRow, blockCol) keys.  Temporaries come from the
+ * stream-ordered allocator.  Column indices inside a row may be in any order. */
 int cuspmm_csr_to_bsr_count(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev,
                             uint32_t M, uint32_t K, uint32_t nnz, uint32_t br, uint32_t bc,
                             uint32_t *blockRowPtrs_dev, uint32_t *numBlocks_host, void *stream);
