@@ -119,16 +119,25 @@ int coo_panel_rowptrs(const uint32_t *rowIdxs, uint32_t rowBase, uint32_t rows, 
 // ------------------------------------------------------------------ sortedness check (precondition of the staged kernels)
 __global__ void csr_check_sorted_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, uint32_t M,
                                         uint32_t K, unsigned int *__restrict__ bad) {
-    // one warp per row: entry i must be > entry i - 1 (strictly ascending) and < K
+    // one warp per row, one coalesced load per entry: entry i must be > entry i - 1 (strictly ascending) and < K; the
+    // predecessor comes from the neighbouring lane (the last lane's value is carried into the next 32 entries)
     const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= M) return;
+    const uint32_t lane = lane_id();
     const uint32_t p0 = __ldg(rowPtrs + r), p1 = __ldg(rowPtrs + r + 1);
     bool wrong = p1 < p0;
-    for (uint32_t i = p0 + lane_id(); i < p1 && !wrong; i += 32) {
-        const uint32_t c = __ldg(colIdxs + i);
-        if (c >= K || (i > p0 && __ldg(colIdxs + i - 1) >= c)) wrong = true;
+    uint32_t carry = 0;
+    bool first = true;
+    for (uint32_t base = p0; base < p1; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t c = i < p1 ? ld_stream(colIdxs + i) : 0xFFFFFFFFu;
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, c, 1);
+        if (lane == 0) prev = carry;
+        if (i < p1 && (c >= K || (!(first && lane == 0) && prev >= c))) wrong = true;
+        carry = __shfl_sync(0xFFFFFFFFu, c, 31);
+        first = false;
     }
-    if (__any_sync(0xFFFFFFFFu, wrong) && lane_id() == 0) atomicAdd(bad, 1u);
+    if (__any_sync(0xFFFFFFFFu, wrong) && lane == 0) atomicAdd(bad, 1u);
 }
 
 // ------------------------------------------------------------------ nnz-balanced row panels

@@ -52,7 +52,7 @@ struct HostPipe {
     cudaStream_t up = nullptr, run = nullptr, down = nullptr;
     cudaEvent_t upDone[kMaxPanels] = {}, runDone[kMaxPanels] = {};
     cudaEvent_t t0 = nullptr, t1 = nullptr, bDone = nullptr, bReady = nullptr;
-    cuspmmBsrTcPlan tc = nullptr;          // cached tensor-core BSR plan buffers are owned by the plan; rebuilt per call
+    cuspmmBsrTcPlan tc = nullptr;          // tensor-core BSR plan of the call in flight (built after the upload, destroyed before return)
     std::mutex mu;
     bool init = false;
     void destroy() {
@@ -420,7 +420,6 @@ extern "C" int cuspmm_spmm_bsr_host(const uint32_t *blockRowPtrs, const uint32_t
     size_t dldb = 0;
     rc = stage_B(hp, B, 0, nullptr, K, N, N, &dB, &dldb);
     if (rc) return rc;
-    if (hp.tc) { cuspmm_bsr_tc_plan_destroy(hp.tc); hp.tc = nullptr; }
     rc = run_panels(hp, parts, rows, N, C, dC,
         [&](uint32_t p) -> int {
             const uint32_t i0 = blockRowPtrs[bs[p]], i1 = blockRowPtrs[bs[p + 1]];
@@ -442,8 +441,13 @@ extern "C" int cuspmm_spmm_bsr_host(const uint32_t *blockRowPtrs, const uint32_t
             if (rc2) return rc2;
             return cuspmm_bsr_tc_run(hp.tc, dC, N, hp.run);
         });
-    if (rc) return rc;
-    return host_end(hp, device_ms);
+    if (rc == CUSPMM_OK) rc = host_end(hp, device_ms);
+    if (hp.tc) {                       // the plan borrows the staging buffers: it does not outlive the call
+        cudaStreamSynchronize(hp.run);
+        cuspmm_bsr_tc_plan_destroy(hp.tc);
+        hp.tc = nullptr;
+    }
+    return rc;
 }
 
 extern "C" int cuspmm_host_pipeline_release(int device) {

@@ -171,7 +171,10 @@ int cuspmm_csr_to_bsr_fill(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_
  * blocks in bf16/fp16 laid out as UMMA core matrices and a scratch for the
  * converted B; `prepare_B` casts + re-tiles B (K x N fp32) once per B, `run`
  * multiplies.  Results equal the fp32 product of the ROUNDED operands up to fp32
- * accumulation order (tolerances: DESIGN.md "parity"). */
+ * accumulation order (tolerances: DESIGN.md "parity").
+ * Lifetime / device: the plan BORROWS blockRowPtrs_dev and blockColIdxs_dev (they must stay valid and unchanged until
+ * plan_destroy); blocks_dev is read only during plan_create.  A plan belongs to the device that was current at plan_create:
+ * prepare_B and run fail with CUSPMM_ERR_INVALID when another device is current. */
 typedef struct cuspmmBsrTcPlan_s *cuspmmBsrTcPlan;
 int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *plan,
                               const uint32_t *blockRowPtrs_dev, const uint32_t *blockColIdxs_dev,

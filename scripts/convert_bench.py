@@ -28,14 +28,22 @@ except Exception:
     PEAK = 6650.0
 
 
+_burn = torch.randn((8192, 8192), device="cuda", dtype=torch.bfloat16)
+
+
 def timed(fn, iters=5):
-    fn(); torch.cuda.synchronize()
-    ts = []
+    """Average over `iters` back-to-back calls between two CUDA events, after a burn that brings the clocks up (a converter
+    timed cold, one call after an idle period, shows 4-5x the time: the GPU sits in a low power state)."""
+    fn()
+    for _ in range(20):
+        torch.mm(_burn, _burn)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(iters):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return statistics.median(ts)
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 
 
 def emit(name, ms, nbytes, **kw):
