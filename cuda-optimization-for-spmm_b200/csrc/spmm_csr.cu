@@ -660,6 +660,19 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
 
     if (variant == 0) variant = csr_select_variant(M, K, nnz, N, vok, SELL);
 
+    // debug guard for the precondition of the staged kernels (ascending columns inside a row): with CUSPMM_CHECK_SORTED set
+    // every call that is about to run variant 3 / 5 / 7 on CSR first verifies it on the device (one pass over colIdxs, a
+    // stream synchronisation) and fails with CUSPMM_ERR_INVALID instead of computing garbage
+    static const bool checkSorted = getenv("CUSPMM_CHECK_SORTED") != nullptr;
+    if (!SELL && checkSorted && (variant == 3 || variant == 5 || variant == 7) && nnz) {
+        uint32_t bad = 0;
+        const int rc = cuspmm_csr_check_sorted(rowPtrs, colIdxs, M, K, &bad, st);
+        if (rc) return rc;
+        if (bad)
+            return set_error(CUSPMM_ERR_INVALID, "%u rows have column indices that are not strictly ascending (or >= K): the staged "
+                             "kernels (variants 3, 5, 7, hence variant 0 on this shape) need sorted rows; use variant 1, 2, 4 or 6", bad);
+    }
+
     // variants 1 and 2 keep their work decomposition but fall back to 32-bit loads when N, ldb/ldc or
     // the base pointers rule out 128-bit ones (N = 21 in data/small_210); variant 4 forces that path
     if ((variant == 1 || variant == 2) && !vok) variant = 4;

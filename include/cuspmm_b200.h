@@ -74,7 +74,9 @@ int cuspmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
  * PRECONDITION for variants 0, 3, 5, 7 (and everything built on them: COO variant 2, sliced ELL, the host-buffer and multi-GPU
  * entry points): column indices ascend strictly inside every row, as the reference's converter writes them
  * (convert_mtx.py:127-143, scipy CSR with sorted indices).  Variants 1, 2, 4, 6 accept any order.  cuspmm_csr_check_sorted
- * verifies it on the device. */
+ * verifies it on the device; with the environment variable CUSPMM_CHECK_SORTED set, every CSR call that is about to run a
+ * staged kernel performs that check first and fails with CUSPMM_ERR_INVALID on unsorted rows (a debug guard: it costs a pass
+ * over colIdxs and a stream synchronisation). */
 #define CUSPMM_CSR_NUM_VARIANTS 7
 int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
                     uint32_t M, uint32_t K, uint32_t nnz,

@@ -325,3 +325,37 @@ def test_cusparse_blocked_ell_baseline_agrees_with_oracle(b):
     den = orc.absprod_csr(orc.csr_from_dense(orc.to_dense(bsr)), B)
     # cuSPARSE runs fp32 Blocked-ELL on TF32 tensor cores (10-bit mantissa operands): observed 3.4e-4 component-wise
     assert orc.max_rel_err(out.cpu().numpy(), orc.spmm_bsr(bsr, B), den) <= 2e-3
+
+
+def test_unsorted_rows_are_refused_under_the_debug_guard():
+    """a legal CSR with unsorted rows must not silently go through the staged kernels.  With
+    CUSPMM_CHECK_SORTED set (read once per process -> child process) the call fails with CUSPMM_ERR_INVALID; the
+    order-agnostic variant 1 still computes the right product."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from __graft_entry__ import load_package
+from conftest import random_csr
+from oracle import oracle as orc
+b = load_package().binding
+a = random_csr(2048, 1024, 0.1, seed=3)
+p0 = int(a.rowPtrs[100]); a.colIdxs[p0], a.colIdxs[p0 + 1] = a.colIdxs[p0 + 1], a.colIdxs[p0]; a.vals[p0], a.vals[p0 + 1] = a.vals[p0 + 1], a.vals[p0]
+B = np.random.default_rng(1).uniform(-1, 1, (1024, 512)).astype(np.float32)
+rp, ci, va, Bd = b.dev_u32(a.rowPtrs), b.dev_u32(a.colIdxs), b.dev_f32(a.vals), b.dev_f32(B)
+for v in (3, 5, 7, 0):
+    try:
+        b.spmm_csr(rp, ci, va, a.M, a.K, Bd, variant=v)
+        print("variant", v, "ran"); sys.exit(1)
+    except b.CuspmmError as e:
+        assert "status 1" in str(e) and "ascending" in str(e), str(e)
+got = b.spmm_csr(rp, ci, va, a.M, a.K, Bd, variant=1).cpu().numpy()
+a.colIdxs[p0], a.colIdxs[p0 + 1] = a.colIdxs[p0 + 1], a.colIdxs[p0]; a.vals[p0], a.vals[p0 + 1] = a.vals[p0 + 1], a.vals[p0]
+assert orc.max_rel_err(got, orc.spmm_csr(a, B), orc.absprod_csr(a, B)) <= 1e-5
+print("guard ok")
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CUSPMM_CHECK_SORTED="1"), capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0 and "guard ok" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
