@@ -119,23 +119,22 @@ int coo_panel_rowptrs(const uint32_t *rowIdxs, uint32_t rowBase, uint32_t rows, 
 // ------------------------------------------------------------------ sortedness check (precondition of the staged kernels)
 __global__ void csr_check_sorted_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, uint32_t M,
                                         uint32_t K, unsigned int *__restrict__ bad) {
-    // one warp per row, one coalesced load per entry: entry i must be > entry i - 1 (strictly ascending) and < K; the
-    // predecessor comes from the neighbouring lane (the last lane's value is carried into the next 32 entries)
+    // one warp per row: entry i must be > entry i - 1 (strictly ascending) and < K.  The predecessor comes from the
+    // neighbouring lane; only lane 0 re-reads the last entry of the previous 32.  Iterations are independent (no carried
+    // value: a version that carried the last lane's entry serialised every load behind a shuffle and ran 20x slower).
     const uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= M) return;
     const uint32_t lane = lane_id();
     const uint32_t p0 = __ldg(rowPtrs + r), p1 = __ldg(rowPtrs + r + 1);
     bool wrong = p1 < p0;
-    uint32_t carry = 0;
-    bool first = true;
+#pragma unroll 4
     for (uint32_t base = p0; base < p1; base += 32) {
         const uint32_t i = base + lane;
-        const uint32_t c = i < p1 ? ld_stream(colIdxs + i) : 0xFFFFFFFFu;
+        const bool live = i < p1;
+        const uint32_t c = live ? __ldg(colIdxs + i) : 0xFFFFFFFFu;
         uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, c, 1);
-        if (lane == 0) prev = carry;
-        if (i < p1 && (c >= K || (!(first && lane == 0) && prev >= c))) wrong = true;
-        carry = __shfl_sync(0xFFFFFFFFu, c, 31);
-        first = false;
+        if (lane == 0 && base > p0) prev = __ldg(colIdxs + i - 1);
+        if (live && (c >= K || (i > p0 && prev >= c))) wrong = true;
     }
     if (__any_sync(0xFFFFFFFFu, wrong) && lane == 0) atomicAdd(bad, 1u);
 }
