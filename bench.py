@@ -414,6 +414,30 @@ def sparse_case(cx, name, M, K, density, N, fmts, steps, seed=618, pre=None):
             rec["cusparse"] = {"alg": "COO_ALG4" if which else "CSR_ALG2", "ms": cus[which], "speedup_vs_cusparse": cus[which] / ms}
             if fmt == "ell":
                 rec["cusparse"]["note"] = "cuSPARSE has no sliced-ELL SpMM: compared with its CSR_ALG2 on the same matrix"
+        if pre is not None and fmt in ("coo", "ell"):        # headline shape: the format's own end-to-end call (host operands)
+            try:
+                C_h = torch.empty((M, N), dtype=torch.float32).pin_memory()
+                B_h = Bd.cpu().pin_memory()
+                if fmt == "coo":
+                    h = [t.cpu().pin_memory() for t in (rows, ci, va)]
+                    call = lambda: b.spmm_coo_host(h[0], h[1], h[2], M, K, B_h, C_h)
+                    h2d = 12 * nnz + 4 * K * N
+                else:
+                    h = [t.cpu().pin_memory() for t in (sp, sc, sv)]
+                    call = lambda: b.spmm_sell_host(h[0], h[1], h[2], M, K, B_h, C_h)
+                    h2d = 8 * int(sc.numel()) + 4 * int(sp.numel()) + 4 * K * N
+                call()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    call()
+                ems = (time.perf_counter() - t0) * 1e3 / 2
+                rec["e2e"] = {"ms_per_step": ems, "value": flops / (ems * 1e-3) / 1e9, "unit": UNIT,
+                              "api": "cuspmm_spmm_coo_host" if fmt == "coo" else "cuspmm_spmm_sell_host",
+                              "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * M * N,
+                              "same_result": bool((C_h.cuda() == Cd).all().item())}
+                del h, C_h, B_h
+            except Exception as ex:
+                rec["e2e"] = {"error": str(ex)[:200]}
         out[fmt] = rec
     return out
 
