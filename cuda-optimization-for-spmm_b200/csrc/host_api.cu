@@ -22,6 +22,11 @@ namespace cuspmm_b200 {
 
 int spmm_csr_dispatch(const uint32_t *, const uint32_t *, const float *, uint32_t, uint32_t, uint32_t,
                       const float *, uint32_t, size_t, float *, size_t, int, cudaStream_t);
+int bsr_tc_plan_create_impl(cuspmmBsrTcPlan *out, const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs, const float *blocks,
+                            uint32_t numBlockRows, uint32_t numBlocks, uint32_t bs, uint32_t K, uint32_t maxN, cuspmmBlockType type,
+                            void *stream, void *blocksQ_ext, void *Bq_ext);      // spmm_bsr_tc.cu
+size_t bsr_tc_blocks_bytes(uint32_t numBlocks, uint32_t bs);
+size_t bsr_tc_B_bytes(uint32_t K, uint32_t bs, uint32_t maxN);
 int coo_panel_rowptrs(const uint32_t *rowIdxs, uint32_t rowBase, uint32_t rows, uint32_t cnt, uint32_t idxBase,
                       uint32_t *rowPtrs, cudaStream_t st);      // convert.cu
 
@@ -49,6 +54,7 @@ constexpr int kMaxPanels = 16;
 // One pipeline (three streams, events, cached device buffers) per device ordinal; used by one call at a time.
 struct HostPipe {
     GrowBuf a0, a1, a2, a3, B, C;          // format arrays (pointers / indices / values / workspace), B, C
+    GrowBuf tcBlocks, tcB;                 // 16-bit re-tiled operands of the tensor-core BSR plan (lent to the plan of the call)
     cudaStream_t up = nullptr, run = nullptr, down = nullptr;
     cudaEvent_t upDone[kMaxPanels] = {}, runDone[kMaxPanels] = {};
     cudaEvent_t t0 = nullptr, t1 = nullptr, bDone = nullptr, bReady = nullptr;
@@ -57,7 +63,7 @@ struct HostPipe {
     bool init = false;
     void destroy() {
         if (tc) { cuspmm_bsr_tc_plan_destroy(tc); tc = nullptr; }
-        a0.release(); a1.release(); a2.release(); a3.release(); B.release(); C.release();
+        a0.release(); a1.release(); a2.release(); a3.release(); B.release(); C.release(); tcBlocks.release(); tcB.release();
         if (init) {
             cudaStreamDestroy(up); cudaStreamDestroy(run); cudaStreamDestroy(down);
             for (int i = 0; i < kMaxPanels; ++i) { cudaEventDestroy(upDone[i]); cudaEventDestroy(runDone[i]); }
@@ -405,6 +411,10 @@ extern "C" int cuspmm_spmm_bsr_host(const uint32_t *blockRowPtrs, const uint32_t
     CUSPMM_CUDA(hp.a1.reserve((size_t)std::max(nb, 1u) * 4));
     CUSPMM_CUDA(hp.a2.reserve((size_t)std::max(nb, 1u) * be * 4));
     CUSPMM_CUDA(hp.C.reserve((size_t)M * N * 4));
+    if (tc) {          // the plan's 16-bit operands live in cached buffers too: no cudaMalloc / cudaFree per call
+        CUSPMM_CUDA(hp.tcBlocks.reserve(bsr_tc_blocks_bytes(nb, br)));
+        CUSPMM_CUDA(hp.tcB.reserve(bsr_tc_B_bytes(K, br, N)));
+    }
     uint32_t *dPtr = static_cast<uint32_t *>(hp.a0.p), *dCol = static_cast<uint32_t *>(hp.a1.p);
     float *dBlk = static_cast<float *>(hp.a2.p), *dC = static_cast<float *>(hp.C.p);
 
@@ -434,8 +444,8 @@ extern "C" int cuspmm_spmm_bsr_host(const uint32_t *blockRowPtrs, const uint32_t
             if (!tc)
                 return cuspmm_spmm_bsr_f32(dPtr + bs[p], dCol, dBlk, bs[p + 1] - bs[p], br, bc, K, dB, N, dldb,
                                            dC + (size_t)rows[p] * N, N, hp.run);
-            int rc2 = cuspmm_bsr_tc_plan_create(&hp.tc, dPtr, dCol, dBlk, numBlockRows, nb, br, K, N,
-                                                variant == 2 ? CUSPMM_BLK_BF16 : CUSPMM_BLK_FP16, hp.run);
+            int rc2 = bsr_tc_plan_create_impl(&hp.tc, dPtr, dCol, dBlk, numBlockRows, nb, br, K, N,
+                                              variant == 2 ? CUSPMM_BLK_BF16 : CUSPMM_BLK_FP16, hp.run, hp.tcBlocks.p, hp.tcB.p);
             if (rc2) return rc2;
             rc2 = cuspmm_bsr_tc_prepare_B(hp.tc, dB, N, dldb, hp.run);
             if (rc2) return rc2;

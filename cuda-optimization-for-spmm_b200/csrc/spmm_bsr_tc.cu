@@ -464,6 +464,7 @@ struct cuspmmBsrTcPlan_s {
     uint32_t numBlockRows = 0, numBlocks = 0, bs = 0, K = 0, Kpad = 0, maxN = 0, maxNpad = 0, N = 0, Npad = 0;
     int type = 0;
     int dev = 0;
+    bool ownsBuffers = true;           // false: blocksQ / Bq were lent by the caller (host pipeline: cached staging buffers)
 };
 
 static bool plan_on_current_device(const cuspmmBsrTcPlan_s *p) {
@@ -471,9 +472,11 @@ static bool plan_on_current_device(const cuspmmBsrTcPlan_s *p) {
     return cudaGetDevice(&dev) == cudaSuccess && dev == p->dev;
 }
 
-extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs,
+namespace cuspmm_b200 {
+// blocksQ_ext / Bq_ext: device buffers lent to the plan (numBlocks * bs * bs and Kpad * maxNpad 16-bit elements); null: the plan allocates
+int bsr_tc_plan_create_impl(cuspmmBsrTcPlan *out, const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs,
                                          const float *blocks, uint32_t numBlockRows, uint32_t numBlocks, uint32_t bs,
-                                         uint32_t K, uint32_t maxN, cuspmmBlockType type, void *stream) {
+                                         uint32_t K, uint32_t maxN, cuspmmBlockType type, void *stream, void *blocksQ_ext, void *Bq_ext) {
     CUSPMM_REQUIRE(out && blockRowPtrs && maxN >= 1, "bad arguments");
     if (bs != 16 && bs != 32)
         return set_error(CUSPMM_ERR_UNSUPPORTED, "tensor-core BSR supports 16x16 and 32x32 blocks (got %u)", bs);
@@ -486,11 +489,17 @@ extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *b
     p->maxN = maxN; p->maxNpad = (maxN + 127) / 128 * 128;
     cudaGetDevice(&p->dev);
     const uint64_t total = (uint64_t)numBlocks * bs * bs;
-    cudaError_t me = cudaMalloc(&p->blocksQ, (total ? total : 1) * 2);
-    if (me == cudaSuccess) me = cudaMalloc(&p->Bq, (size_t)p->Kpad * p->maxNpad * 2);
-    if (me != cudaSuccess) {
-        cudaFree(p->blocksQ); cudaFree(p->Bq); delete p;
-        return set_error(CUSPMM_ERR_CUDA, "cudaMalloc of the tensor-core BSR plan failed: %s", cudaGetErrorString(me));
+    if (blocksQ_ext && Bq_ext) {
+        p->blocksQ = static_cast<uint16_t *>(blocksQ_ext);
+        p->Bq = static_cast<uint16_t *>(Bq_ext);
+        p->ownsBuffers = false;
+    } else {
+        cudaError_t me = cudaMalloc(&p->blocksQ, (total ? total : 1) * 2);
+        if (me == cudaSuccess) me = cudaMalloc(&p->Bq, (size_t)p->Kpad * p->maxNpad * 2);
+        if (me != cudaSuccess) {
+            cudaFree(p->blocksQ); cudaFree(p->Bq); delete p;
+            return set_error(CUSPMM_ERR_CUDA, "cudaMalloc of the tensor-core BSR plan failed: %s", cudaGetErrorString(me));
+        }
     }
     if (total) {
         const unsigned grid = (unsigned)((total + 255) / 256);
@@ -498,13 +507,26 @@ extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *b
         else bsrtc::tile_blocks_kernel<__half><<<grid, 256, 0, st>>>(blocks, total, bs, p->blocksQ);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
-            cudaFree(p->blocksQ); cudaFree(p->Bq); delete p;
+            if (p->ownsBuffers) { cudaFree(p->blocksQ); cudaFree(p->Bq); }
+            delete p;
             return set_error(CUSPMM_ERR_CUDA, "launch of tile_blocks_kernel failed: %s", cudaGetErrorString(e));
         }
         count_launch();
     }
     *out = p;
     return CUSPMM_OK;
+}
+size_t bsr_tc_blocks_bytes(uint32_t numBlocks, uint32_t bs) { return (size_t)(numBlocks ? numBlocks : 1) * bs * bs * 2; }
+size_t bsr_tc_B_bytes(uint32_t K, uint32_t bs, uint32_t maxN) {
+    return (size_t)((K + bs - 1) / bs * bs) * ((maxN + 127) / 128 * 128) * 2;
+}
+} // namespace cuspmm_b200
+
+extern "C" int cuspmm_bsr_tc_plan_create(cuspmmBsrTcPlan *out, const uint32_t *blockRowPtrs, const uint32_t *blockColIdxs,
+                                         const float *blocks, uint32_t numBlockRows, uint32_t numBlocks, uint32_t bs,
+                                         uint32_t K, uint32_t maxN, cuspmmBlockType type, void *stream) {
+    return cuspmm_b200::bsr_tc_plan_create_impl(out, blockRowPtrs, blockColIdxs, blocks, numBlockRows, numBlocks, bs, K, maxN, type,
+                                                stream, nullptr, nullptr);
 }
 
 extern "C" int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan p, const float *B, uint32_t N, size_t ldb, void *stream) {
@@ -578,8 +600,10 @@ extern "C" int cuspmm_bsr_tc_run(cuspmmBsrTcPlan p, float *C, size_t ldc, void *
 
 extern "C" int cuspmm_bsr_tc_plan_destroy(cuspmmBsrTcPlan p) {
     if (!p) return CUSPMM_OK;
-    cudaFree(p->blocksQ);
-    cudaFree(p->Bq);
+    if (p->ownsBuffers) {
+        cudaFree(p->blocksQ);
+        cudaFree(p->Bq);
+    }
     delete p;
     return CUSPMM_OK;
 }
