@@ -226,27 +226,36 @@ bsr_tc_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *__restr
 // of C (one UMMA M-tile) and walks the UNION of the panel's block columns in ascending order: the slab of B belonging to block
 // column j is fetched ONCE and multiplied against every block row of the panel that stores a block in column j.  At 10 %
 // block density a panel of 11 block rows touches 69 % of the block columns for 1.1 blocks per column: 0.62 slabs per block
-// instead of 1 (P = 16: 0.51).  Accumulators: D_p = TMEM columns [p * bs, (p + 1) * bs), P * bs <= 512.
-//   warp 0  producer: P cursors (lane = block row), REDUX.min = next block column of the union, ballot = the rows that hit
-//           it; per stage: the 128-column slab of that block column (bs/8 bulk copies of 2 KB) + up to kHitsPerStage blocks;
-//           the hit mask travels in shared memory beside the stage
-//   warp 1  MMA issuer: for every hit row p: D_p += slab^T x block^T (bs/16 x tcgen05.mma M128 N=bs K16); commit frees the stage
-//   warps 2..5 epilogue: tcgen05.ld.x16 per block row -> 128-byte row stores
+// instead of 1 (P = 22 at 16x16: 0.41).  Accumulators: D_p = TMEM columns [p * bs, (p + 1) * bs), P * bs <= 512.
+//   warp 0      walker: P cursors (lane = block row) over the panel's block column indices (staged in shared memory), REDUX.min =
+//               next block column of the union, ballot = the rows that hit it; writes a stage descriptor (column, hit mask, block ids)
+//   warps 2..5  copiers: copier w fills the stages i = w (mod 4) with cp.async (16 bytes per lane: the slab's 2 KB pieces and the
+//               hit blocks), one commit group per stage, and publishes a stage once its group has completed
+//               (cp.async.wait_group + fence.proxy.async, the operands are read by the tensor core through the async proxy);
+//               afterwards the same warps run the epilogue (tcgen05.ld.x16 per block row -> 128-byte row stores)
+//   warp 1      MMA issuer: for every hit row p: D_p += slab^T x block^T (bs/16 x tcgen05.mma M128 N=bs K16); commit frees the stage
+// First version (TMA bulk copies issued by the walker warp, profiles/r02_bsr_panel_probe.jsonl): 0.60 ms at 32x32 against 0.18 ms
+// for the block-row kernel -- a stage was 5-6 small bulk copies and one warp retires about one bulk copy per ~200 clocks.
 // Grid = (ceil(numBlockRows / P), Npad / 128); the host picks P so that the grid is just under a whole number of waves.
 constexpr int kHitsPerStage = 4;
+constexpr int kCopiers = 4;
 template <int BS>
 struct PanelSmem {
-    static constexpr int kStages = BS == 16 ? 20 : 12;
+    static constexpr int kStages = BS == 16 ? 24 : 12;
     static constexpr uint32_t kBlockBytes = BS * BS * 2;
     static constexpr uint32_t kSlabBytes = BS * 128 * 2;                     // bs k-rows x 128 n x 16 bit
     static constexpr uint32_t kStageBytes = kSlabBytes + kHitsPerStage * kBlockBytes;
+    static constexpr uint32_t kDescWords = 8;                                // column, hit mask, block ids[4], pad
     // the panel's block column indices, staged once: the union walk is a serial chain (min over the cursors -> hit mask ->
-    // advance -> next index), and with the indices in global memory every step paid an L2 round trip (first version: 0.68 ms
-    // against 0.18 ms for the block-row kernel); indices beyond the buffer (very dense panels) are still read from global memory
+    // advance -> next index); indices beyond the buffer (very dense panels) are read from global memory
     static constexpr uint32_t kIdxCap = 6144;
-    static constexpr uint32_t kTotal = kStages * kStageBytes + (2 * kStages + 1) * 8 + kStages * 4 + kIdxCap * 4 + 16 + 128;
+    static constexpr uint32_t kTotal = kStages * kStageBytes + (3 * kStages + 1) * 8 + kStages * kDescWords * 4 + kIdxCap * 4 + 16 + 128;
     static_assert(kTotal <= 232448, "more than 227 KB of shared memory");
 };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 
 template <int BS, int FMT>
 __global__ void __launch_bounds__(kThreads)
@@ -258,11 +267,12 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
     extern __shared__ __align__(128) unsigned char smem[];
     using S = PanelSmem<BS>;
     constexpr int kStages = S::kStages;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * S::kStageBytes);
-    uint64_t *empty = full + kStages;
-    uint64_t *accum_full = empty + kStages;
-    uint32_t *meta = reinterpret_cast<uint32_t *>(accum_full + 1);          // hit mask of each stage (0 = end of the walk)
-    uint32_t *idx_s = meta + kStages;                                       // blockColIdxs[base .. base + kIdxCap)
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + kStages * S::kStageBytes);   // stage operands landed   (copier -> issuer)
+    uint64_t *empty = full + kStages;                                                   // stage consumed          (issuer -> walker)
+    uint64_t *desc_full = empty + kStages;                                              // descriptor written      (walker -> copier)
+    uint64_t *accum_full = desc_full + kStages;
+    uint32_t *desc = reinterpret_cast<uint32_t *>(accum_full + 1);                      // [kStages][kDescWords]
+    uint32_t *idx_s = desc + kStages * S::kDescWords;                                   // blockColIdxs[base .. base + kIdxCap)
     uint32_t *tmem_slot = idx_s + S::kIdxCap;
 
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
@@ -276,7 +286,7 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
     }
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); mbar_init(desc_full + s, 1); }
         mbar_init(accum_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -290,7 +300,7 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ producer: union walk over the panel's block columns
+        // ------------------------------------------------------------------ walker: the union of the panel's block columns
         uint32_t cur = 0, end = 0;
         if (lane < P && R0 + lane < numBlockRows) {
             cur = __ldg(blockRowPtrs + R0 + lane);
@@ -303,6 +313,11 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
         };
         uint32_t col = col_at(cur);
         uint32_t i = 0;
+        auto open_stage = [&]() -> uint32_t * {          // wait until stage i % kStages has been consumed, return its descriptor
+            const uint32_t s = i % kStages, it = i / kStages;
+            if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+            return desc + s * S::kDescWords;
+        };
         while (true) {
             const uint32_t j = __reduce_min_sync(0xFFFFFFFFu, col);
             if (j == 0xFFFFFFFFu) break;
@@ -311,26 +326,11 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
                 uint32_t take = 0, h = hit;
 #pragma unroll
                 for (int k = 0; k < kHitsPerStage; ++k) { take |= h & (0u - h); h &= h - 1u; }
-                const uint32_t s = i % kStages, it = i / kStages;
-                if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
-                unsigned char *slab = smem + s * S::kStageBytes;
-                unsigned char *blk = slab + S::kSlabBytes;
-                if (lane == 0) {
-                    meta[s] = take;
-                    mbar_expect_tx(full + s, S::kSlabBytes + (uint32_t)__popc(take) * S::kBlockBytes);
-                }
+                uint32_t *d = open_stage();
+                if ((take >> lane) & 1u) d[2 + __popc(take & ((1u << lane) - 1u))] = cur;      // block ids in slot order
+                if (lane == 0) { d[0] = j; d[1] = take; }
                 __syncwarp();
-                // the copies of a stage are issued by different lanes: lanes 31, 30, .. the bs/8 pieces of the slab (the panel has
-                // at most 32 - bs/8 block rows when those lanes are rows too -- they then issue both), hit rows their block
-                if (lane >= 32u - BS / 8) {
-                    const uint32_t kb = 31u - lane;
-                    const uint16_t *src = Bq + ((size_t)j * (BS / 8) * Npad + n0) * 8;
-                    bulk_g2s(slab + (size_t)kb * 128 * 16, src + (size_t)kb * Npad * 8, 128 * 16, full + s);
-                }
-                if ((take >> lane) & 1u) {
-                    const uint32_t slot = (uint32_t)__popc(take & ((1u << lane) - 1u));
-                    bulk_g2s(blk + slot * S::kBlockBytes, blocksQ + (size_t)cur * BS * BS, S::kBlockBytes, full + s);
-                }
+                if (lane == 0) pipe::mbar_arrive(desc_full + i % kStages);
                 hit &= ~take;
                 ++i;
             }
@@ -339,14 +339,14 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
                 col = col_at(cur);
             }
         }
-        // end marker: a stage with an empty hit mask and no bytes
-        {
-            const uint32_t s = i % kStages, it = i / kStages;
-            if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
+        // end markers: one per copier (an empty hit mask); the issuer stops at the first
+        for (int k = 0; k < kCopiers; ++k) {
+            uint32_t *d = open_stage();
             if (lane == 0) {
-                meta[s] = 0u;
-                pipe::mbar_arrive(full + s);
+                d[1] = 0u;
+                pipe::mbar_arrive(desc_full + i % kStages);
             }
+            ++i;
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
@@ -356,8 +356,9 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
             for (uint32_t i = 0;; ++i) {
                 const uint32_t s = i % kStages, it = i / kStages;
                 mbar_wait(full + s, it & 1);
-                uint32_t m = meta[s];
+                uint32_t m = desc[s * S::kDescWords + 1];
                 if (m == 0u) break;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async (generic proxy) writes -> tensor-core reads
                 tc_fence_after();
                 const uint32_t slab = smem_u32(smem + s * S::kStageBytes);
                 uint32_t blk = slab + S::kSlabBytes;
@@ -378,7 +379,58 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
             umma_commit(accum_full);             // all accumulators final
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ copiers (warps 2..5), then the epilogue
+        const uint32_t w = warp - 2;
+        // LAG commit groups (= stages) of this warp stay in flight: a stage is published when the stage issued LAG rounds later
+        // has been queued (with one group in flight per copier the kernel ran at 16 B/clk per SM: memory latency, not bandwidth)
+        constexpr int LAG = BS == 16 ? 4 : 2;
+        uint32_t pend[LAG];
+#pragma unroll
+        for (int k = 0; k < LAG; ++k) pend[k] = 0xFFFFFFFFu;      // pend[0] = oldest
+        for (uint32_t i = w;; i += kCopiers) {
+            const uint32_t s = i % kStages;
+            mbar_wait(desc_full + s, (i / kStages) & 1);
+            const uint32_t *d = desc + s * S::kDescWords;
+            const uint32_t j = d[0], take = d[1];
+            if (take == 0u) {                    // end of the walk: publish what is still in flight, pass the marker on
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < LAG; ++k)
+                        if (pend[k] != 0xFFFFFFFFu) pipe::mbar_arrive(full + pend[k]);
+                    pipe::mbar_arrive(full + s);
+                }
+                break;
+            }
+            const uint32_t slab = smem_u32(smem + s * S::kStageBytes);
+            const uint16_t *src = Bq + ((size_t)j * (BS / 8) * Npad + n0) * 8;
+#pragma unroll
+            for (int kb = 0; kb < BS / 8; ++kb)
+#pragma unroll
+                for (int r = 0; r < 4; ++r)      // 128 columns x 16 bytes per k-group
+                    cp_async16(slab + kb * 2048 + (r * 32 + lane) * 16, src + ((size_t)kb * Npad + r * 32 + lane) * 8);
+            const uint32_t hits = (uint32_t)__popc(take);
+            for (uint32_t h = 0; h < hits; ++h) {
+                const uint16_t *bsrc = blocksQ + (size_t)d[2 + h] * BS * BS;
+                const uint32_t bdst = slab + S::kSlabBytes + h * S::kBlockBytes;
+#pragma unroll
+                for (int r = 0; r < (int)(S::kBlockBytes / 512); ++r)
+                    cp_async16(bdst + (r * 32 + lane) * 16, bsrc + (r * 32 + lane) * 8);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (pend[0] != 0xFFFFFFFFu) {        // the stage issued LAG rounds earlier has landed once at most LAG groups are pending
+                asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) pipe::mbar_arrive(full + pend[0]);
+            }
+#pragma unroll
+            for (int k = 0; k + 1 < LAG; ++k) pend[k] = pend[k + 1];
+            pend[LAG - 1] = s;
+        }
+        // ------------------------------------------------------------------ epilogue
         const uint32_t q = warp & 3;             // TMEM lane quarter this warp may access
         mbar_wait(accum_full, 0);
         tc_fence_after();
@@ -547,12 +599,16 @@ extern "C" int cuspmm_bsr_tc_prepare_B(cuspmmBsrTcPlan p, const float *B, uint32
 template <int BS, int FMT>
 static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
     // The block-row kernel is the default.  The panel kernel (union walk) is correct (tests/test_gpu_bsr_tc.py runs it through
-    // the hook) but slower as built: 0.60 ms (32x32, P = 11) / 1.41 ms (16x16, P = 22) against 0.18 / 0.28 ms on BASELINE
-    // configs[3] (profiles/r02_bsr_panel_probe.jsonl).  Its stages are many SMALL bulk copies (2 KB slab pieces of a 128-column
-    // tile, 0.5-2 KB blocks) and the TMA unit retires roughly one bulk copy per ~200 clk per SM whatever its size (ncu: L2 -> SM
-    // 1.7 TB/s, every pipe idle, the MMA issuer waiting for data), so the bytes saved by sharing slabs are lost several times
-    // over; the block-row kernel moves 34 KB per two copies.  Tuning hooks: CUSPMM_BSR_PANEL = 1 selects the panel kernel,
-    // CUSPMM_BSR_P its panel height.
+    // the hook) but slower as built, on BASELINE configs[3] (profiles/r02_bsr_panel_probe.jsonl; block-row kernel 0.18 / 0.28 ms):
+    //   TMA bulk copies issued by the walking warp           0.60 ms (32x32, P = 11) / 1.41 ms (16x16, P = 22): 5-6 small copies per
+    //                                                        stage, one warp retires about one bulk copy per ~200 clk
+    //   walker + four cp.async copier warps, 2-4 groups deep 0.40 ms / 0.99 ms: the copiers now starve for DESCRIPTORS (54 % of the
+    //                                                        stall samples on desc_full): the union walk is one serial chain per
+    //                                                        stage (LDS -> REDUX.min -> ballot -> descriptor stores -> arrive,
+    //                                                        ~500 clk) and a panel has 600 (32x32) to 1700 (16x16) stages
+    // What it would take: the column range split over four walking-and-copying warps (the issuer merging their stage streams
+    // round-robin), or the walk done word-parallel on per-row bitmaps.  Tuning hooks: CUSPMM_BSR_PANEL = 1 selects the panel
+    // kernel, CUSPMM_BSR_P its panel height.
     static const int forcePanel = getenv("CUSPMM_BSR_PANEL") ? atoi(getenv("CUSPMM_BSR_PANEL")) : -1;
     static const int forceP = getenv("CUSPMM_BSR_P") ? atoi(getenv("CUSPMM_BSR_P")) : 0;
     const uint32_t ytiles = p->Npad / 128;
