@@ -246,10 +246,11 @@ struct PanelSmem {
     static constexpr uint32_t kSlabBytes = BS * 128 * 2;                     // bs k-rows x 128 n x 16 bit
     static constexpr uint32_t kStageBytes = kSlabBytes + kHitsPerStage * kBlockBytes;
     static constexpr uint32_t kDescWords = 8;                                // column, hit mask, block ids[4], pad
-    // the panel's block column indices, staged once: the union walk is a serial chain (min over the cursors -> hit mask ->
-    // advance -> next index); indices beyond the buffer (very dense panels) are read from global memory
-    static constexpr uint32_t kIdxCap = 6144;
-    static constexpr uint32_t kTotal = kStages * kStageBytes + (3 * kStages + 1) * 8 + kStages * kDescWords * 4 + kIdxCap * 4 + 16 + 128;
+    // one bitmap of block columns per block row of the panel (built once by the whole CTA): the union walk then needs, per 32
+    // block columns, one LDS + one REDUX.or, and per block column of the union one ballot -- instead of LDS -> REDUX.min ->
+    // ballot per column on cursors.  32 rows x 64 words: panels of matrices with at most 2048 block columns.
+    static constexpr uint32_t kBmWords = 64;
+    static constexpr uint32_t kTotal = kStages * kStageBytes + (3 * kStages + 1) * 8 + kStages * kDescWords * 4 + 32 * kBmWords * 4 + 16 + 128;
     static_assert(kTotal <= 232448, "more than 227 KB of shared memory");
 };
 
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kThreads)
 bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *__restrict__ blockColIdxs,
                     const uint16_t *__restrict__ blocksQ,   // [numBlocks][BS/8][BS][8]
                     const uint16_t *__restrict__ Bq,        // [Kpad/8][Npad][8]
-                    uint32_t numBlockRows, uint32_t P, uint32_t tmemCols, uint32_t Npad, uint32_t N,
+                    uint32_t numBlockRows, uint32_t numBlockCols, uint32_t P, uint32_t tmemCols, uint32_t Npad, uint32_t N,
                     float *__restrict__ C, size_t ldc) {
     extern __shared__ __align__(128) unsigned char smem[];
     using S = PanelSmem<BS>;
@@ -272,17 +273,21 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
     uint64_t *desc_full = empty + kStages;                                              // descriptor written      (walker -> copier)
     uint64_t *accum_full = desc_full + kStages;
     uint32_t *desc = reinterpret_cast<uint32_t *>(accum_full + 1);                      // [kStages][kDescWords]
-    uint32_t *idx_s = desc + kStages * S::kDescWords;                                   // blockColIdxs[base .. base + kIdxCap)
-    uint32_t *tmem_slot = idx_s + S::kIdxCap;
+    uint32_t *bm = desc + kStages * S::kDescWords;                                      // [32 rows][kBmWords]: block columns of each panel row
+    uint32_t *tmem_slot = bm + 32 * S::kBmWords;
 
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t R0 = blockIdx.x * P;
     const uint32_t n0 = blockIdx.y * 128;
-    const uint32_t idxBase = __ldg(blockRowPtrs + R0);
-    {
-        const uint32_t idxEnd = __ldg(blockRowPtrs + min(R0 + P, numBlockRows));
-        const uint32_t cnt = min(idxEnd - idxBase, S::kIdxCap);
-        for (uint32_t t = threadIdx.x; t < cnt; t += kThreads) idx_s[t] = __ldg(blockColIdxs + idxBase + t);
+    const uint32_t bmW = (((numBlockCols + 31u) >> 5) < S::kBmWords) ? ((numBlockCols + 31u) >> 5) : S::kBmWords;
+    for (uint32_t t = threadIdx.x; t < 32 * S::kBmWords; t += kThreads) bm[t] = 0u;
+    __syncthreads();
+    for (uint32_t p = 0; p < P && R0 + p < numBlockRows; ++p) {
+        const uint32_t b0 = __ldg(blockRowPtrs + R0 + p), b1 = __ldg(blockRowPtrs + R0 + p + 1);
+        for (uint32_t t = b0 + threadIdx.x; t < b1; t += kThreads) {
+            const uint32_t c = __ldg(blockColIdxs + t);
+            atomicOr(bm + p * S::kBmWords + (c >> 5), 1u << (c & 31u));
+        }
     }
 
     if (threadIdx.x == 0) {
@@ -301,42 +306,38 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
 
     if (warp == 0) {
         // ------------------------------------------------------------------ walker: the union of the panel's block columns
-        uint32_t cur = 0, end = 0;
-        if (lane < P && R0 + lane < numBlockRows) {
-            cur = __ldg(blockRowPtrs + R0 + lane);
-            end = __ldg(blockRowPtrs + R0 + lane + 1);
-        }
-        auto col_at = [&](uint32_t c) -> uint32_t {
-            if (c >= end) return 0xFFFFFFFFu;
-            const uint32_t o = c - idxBase;
-            return o < S::kIdxCap ? idx_s[o] : __ldg(blockColIdxs + c);
-        };
-        uint32_t col = col_at(cur);
+        // lane = block row of the panel; cur = its next block (block columns ascend inside a block row, as the converter and
+        // scipy write them, so the bitmap order is the storage order)
+        uint32_t cur = 0;
+        if (lane < P && R0 + lane < numBlockRows) cur = __ldg(blockRowPtrs + R0 + lane);
         uint32_t i = 0;
         auto open_stage = [&]() -> uint32_t * {          // wait until stage i % kStages has been consumed, return its descriptor
             const uint32_t s = i % kStages, it = i / kStages;
             if (it > 0) mbar_wait(empty + s, (it - 1) & 1);
             return desc + s * S::kDescWords;
         };
-        while (true) {
-            const uint32_t j = __reduce_min_sync(0xFFFFFFFFu, col);
-            if (j == 0xFFFFFFFFu) break;
-            uint32_t hit = __ballot_sync(0xFFFFFFFFu, col == j);
-            while (hit) {
-                uint32_t take = 0, h = hit;
+        for (uint32_t w = 0; w < bmW; ++w) {
+            const uint32_t word = bm[lane * S::kBmWords + w];
+            uint32_t uni = __reduce_or_sync(0xFFFFFFFFu, word);
+            while (uni) {
+                const uint32_t bit = (uint32_t)__ffs((int)uni) - 1u;
+                uni &= uni - 1u;
+                const uint32_t j = w * 32u + bit;
+                const bool mine = (word >> bit) & 1u;
+                uint32_t hit = __ballot_sync(0xFFFFFFFFu, mine);
+                while (hit) {
+                    uint32_t take = 0, h = hit;
 #pragma unroll
-                for (int k = 0; k < kHitsPerStage; ++k) { take |= h & (0u - h); h &= h - 1u; }
-                uint32_t *d = open_stage();
-                if ((take >> lane) & 1u) d[2 + __popc(take & ((1u << lane) - 1u))] = cur;      // block ids in slot order
-                if (lane == 0) { d[0] = j; d[1] = take; }
-                __syncwarp();
-                if (lane == 0) pipe::mbar_arrive(desc_full + i % kStages);
-                hit &= ~take;
-                ++i;
-            }
-            if (col == j) {
-                ++cur;
-                col = col_at(cur);
+                    for (int k = 0; k < kHitsPerStage; ++k) { take |= h & (0u - h); h &= h - 1u; }
+                    uint32_t *d = open_stage();
+                    if ((take >> lane) & 1u) d[2 + __popc(take & ((1u << lane) - 1u))] = cur;      // block ids in slot order
+                    if (lane == 0) { d[0] = j; d[1] = take; }
+                    __syncwarp();
+                    if (lane == 0) pipe::mbar_arrive(desc_full + i % kStages);
+                    hit &= ~take;
+                    ++i;
+                }
+                if (mine) ++cur;
             }
         }
         // end markers: one per copier (an empty hit mask); the issuer stops at the first
@@ -358,7 +359,8 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
                 mbar_wait(full + s, it & 1);
                 uint32_t m = desc[s * S::kDescWords + 1];
                 if (m == 0u) break;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // cp.async (generic proxy) writes -> tensor-core reads
+                // (the generic -> async proxy fence is executed by the copier warps after cp.async.wait_group, before they
+                //  arrive on `full`; a second one here costs the issuer several hundred clocks per stage)
                 tc_fence_after();
                 const uint32_t slab = smem_u32(smem + s * S::kStageBytes);
                 uint32_t blk = slab + S::kSlabBytes;
@@ -381,29 +383,45 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
     } else {
         // ------------------------------------------------------------------ copiers (warps 2..5), then the epilogue
         const uint32_t w = warp - 2;
-        // LAG commit groups (= stages) of this warp stay in flight: a stage is published when the stage issued LAG rounds later
-        // has been queued (with one group in flight per copier the kernel ran at 16 B/clk per SM: memory latency, not bandwidth)
+        // Up to LAG commit groups (= stages) of this warp are in flight.  A stage is published (fence.proxy.async + arrive on
+        // `full`) as soon as its group has completed: when LAG groups are pending, or whenever the next descriptor is not there
+        // yet.  (Publishing a stage only when a LATER one was issued tied the issuer to the walker: with the ring 4 * LAG stages
+        // short the whole pipeline advanced 8 stages per round trip.)
         constexpr int LAG = BS == 16 ? 4 : 2;
         uint32_t pend[LAG];
+        int npend = 0;
 #pragma unroll
         for (int k = 0; k < LAG; ++k) pend[k] = 0xFFFFFFFFu;      // pend[0] = oldest
-        for (uint32_t i = w;; i += kCopiers) {
+        auto retire_oldest = [&]() {              // npend >= 1: wait until only the npend - 1 younger groups are pending
+            if (npend == 1) asm volatile("cp.async.wait_group 0;" ::: "memory");
+            else if (npend == 2) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else if (npend == 3) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else asm volatile("cp.async.wait_group 3;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) pipe::mbar_arrive(full + pend[0]);
+#pragma unroll
+            for (int k = 0; k + 1 < LAG; ++k) pend[k] = pend[k + 1];
+            pend[LAG - 1] = 0xFFFFFFFFu;
+            --npend;
+        };
+        static_assert(LAG <= 4, "retire_oldest covers up to four pending groups");
+        for (uint32_t i = w;;) {
             const uint32_t s = i % kStages;
-            mbar_wait(desc_full + s, (i / kStages) & 1);
+            if (npend > 0) {                     // something in flight: do not block on the walker, retire instead
+                const bool ready = __shfl_sync(0xFFFFFFFFu, pipe::mbar_try_wait(desc_full + s, (i / kStages) & 1) ? 1 : 0, 0) != 0;
+                if (!ready) { retire_oldest(); continue; }
+            } else {
+                mbar_wait(desc_full + s, (i / kStages) & 1);
+            }
             const uint32_t *d = desc + s * S::kDescWords;
             const uint32_t j = d[0], take = d[1];
             if (take == 0u) {                    // end of the walk: publish what is still in flight, pass the marker on
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int k = 0; k < LAG; ++k)
-                        if (pend[k] != 0xFFFFFFFFu) pipe::mbar_arrive(full + pend[k]);
-                    pipe::mbar_arrive(full + s);
-                }
+                while (npend > 0) retire_oldest();
+                if (lane == 0) pipe::mbar_arrive(full + s);
                 break;
             }
+            if (npend == LAG) retire_oldest();   // make room: at most LAG groups in flight
             const uint32_t slab = smem_u32(smem + s * S::kStageBytes);
             const uint16_t *src = Bq + ((size_t)j * (BS / 8) * Npad + n0) * 8;
 #pragma unroll
@@ -420,15 +438,11 @@ bsr_tc_panel_kernel(const uint32_t *__restrict__ blockRowPtrs, const uint32_t *_
                     cp_async16(bdst + (r * 32 + lane) * 16, bsrc + (r * 32 + lane) * 8);
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            if (pend[0] != 0xFFFFFFFFu) {        // the stage issued LAG rounds earlier has landed once at most LAG groups are pending
-                asm volatile("cp.async.wait_group %0;" ::"n"(LAG) : "memory");
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) pipe::mbar_arrive(full + pend[0]);
-            }
 #pragma unroll
-            for (int k = 0; k + 1 < LAG; ++k) pend[k] = pend[k + 1];
-            pend[LAG - 1] = s;
+            for (int k = 0; k < LAG; ++k)
+                if (k == npend) pend[k] = s;
+            ++npend;
+            i += kCopiers;
         }
         // ------------------------------------------------------------------ epilogue
         const uint32_t q = warp & 3;             // TMEM lane quarter this warp may access
@@ -602,13 +616,13 @@ static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
     // the hook) but slower as built, on BASELINE configs[3] (profiles/r02_bsr_panel_probe.jsonl; block-row kernel 0.18 / 0.28 ms):
     //   TMA bulk copies issued by the walking warp           0.60 ms (32x32, P = 11) / 1.41 ms (16x16, P = 22): 5-6 small copies per
     //                                                        stage, one warp retires about one bulk copy per ~200 clk
-    //   walker + four cp.async copier warps, 2-4 groups deep 0.40 ms / 0.99 ms: the copiers now starve for DESCRIPTORS (54 % of the
-    //                                                        stall samples on desc_full): the union walk is one serial chain per
-    //                                                        stage (LDS -> REDUX.min -> ballot -> descriptor stores -> arrive,
-    //                                                        ~500 clk) and a panel has 600 (32x32) to 1700 (16x16) stages
-    // What it would take: the column range split over four walking-and-copying warps (the issuer merging their stage streams
-    // round-robin), or the walk done word-parallel on per-row bitmaps.  Tuning hooks: CUSPMM_BSR_PANEL = 1 selects the panel
-    // kernel, CUSPMM_BSR_P its panel height.
+    //   walker + four cp.async copier warps                  0.40 ms / 0.98 ms -- and it stayed there through four changes of the
+    //       pipeline (deeper commit groups, a word-parallel walk on per-row bitmaps, no proxy fence in the issuer, stages published
+    //       as soon as they land): ~620 clocks per stage whatever the stage does.  Little's law: a panel CTA has one 12-stage ring
+    //       of 16 KB stages that are on average 64 % full = 120 KB in flight, and a stage lives ~7 400 clocks (L2 latency under
+    //       load + three mbarrier hand-offs: walker -> copier -> issuer -> walker), i.e. 16 B/clk per SM; the block-row kernel keeps
+    //       204 KB in flight for ~4 500 clocks = 45 B/clk.  Needing 0.62x the bytes does not pay for moving them at 0.37x the rate.
+    // Tuning hooks: CUSPMM_BSR_PANEL = 1 selects the panel kernel, CUSPMM_BSR_P its panel height.
     static const int forcePanel = getenv("CUSPMM_BSR_PANEL") ? atoi(getenv("CUSPMM_BSR_PANEL")) : -1;
     static const int forceP = getenv("CUSPMM_BSR_P") ? atoi(getenv("CUSPMM_BSR_P")) : 0;
     const uint32_t ytiles = p->Npad / 128;
@@ -624,7 +638,7 @@ static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
     }
     if (forceP > 0) P = (uint32_t)forceP > Pmax ? Pmax : (uint32_t)forceP;
     if (P < 1) P = 1;
-    const bool usePanel = forcePanel > 0;
+    const bool usePanel = forcePanel > 0 && p->Kpad / BS <= 32u * bsrtc::PanelSmem<BS>::kBmWords;     // bitmaps hold 2048 block columns
     if (usePanel) {
         auto kern = bsrtc::bsr_tc_panel_kernel<BS, FMT>;
         CUSPMM_CUDA(set_smem_once(kern, bsrtc::PanelSmem<BS>::kTotal));
@@ -632,7 +646,7 @@ static int launch_tc(cuspmmBsrTcPlan p, float *C, size_t ldc, cudaStream_t st) {
         while (cols < P * BS) cols <<= 1;
         dim3 grid((p->numBlockRows + P - 1) / P, ytiles);
         kern<<<grid, bsrtc::kThreads, bsrtc::PanelSmem<BS>::kTotal, st>>>(p->blockRowPtrs, p->blockColIdxs, p->blocksQ, p->Bq,
-                                                                           p->numBlockRows, P, cols, p->Npad, p->N, C, ldc);
+                                                                           p->numBlockRows, p->Kpad / BS, P, cols, p->Npad, p->N, C, ldc);
         CUSPMM_LAUNCH_CHECK("bsr_tc_panel_kernel");
         return CUSPMM_OK;
     }
