@@ -151,7 +151,7 @@ def spmm_csr(rowPtrs, colIdxs, vals, M, K, B, variant=0, out=None, nnz=None, all
 
 
 CSR_KERNEL_NAMES = {1: "csr_rowsplit_vec", 2: "csr_subwarp_vec", 3: "csr_staged", 4: "csr_rowsplit_scalar", 5: "csr_dual",
-                    6: "csr_nnzsplit", 7: "csr_quad"}
+                    6: "csr_nnzsplit", 7: "csr_quad", 8: "csr_tensor"}
 
 
 def csr_selected_variant(M, K, nnz, N, sell=False):

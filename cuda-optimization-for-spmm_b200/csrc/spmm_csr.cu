@@ -590,6 +590,9 @@ template <bool SELL>
 int spmm_rows_quad(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint64_t nnz,
                    const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
 void quad_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_per_cta);
+// variant 8: A tiles made dense in shared memory, tcgen05.mma with a three-product tf32 / bf16 split (spmm_csr_tc.cu); CSR only
+int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
+                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
 // variant 6: nnz split that cuts rows, ordered carry fix-up (spmm_csr_split.cu); needs workspace
 size_t spmm_csr_split_workspace(uint32_t nnz, uint32_t N);
 int spmm_csr_split(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
@@ -661,16 +664,16 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
     if (variant == 0) variant = csr_select_variant(M, K, nnz, N, vok, SELL);
 
     // debug guard for the precondition of the staged kernels (ascending columns inside a row): with CUSPMM_CHECK_SORTED set
-    // every call that is about to run variant 3 / 5 / 7 on CSR first verifies it on the device (one pass over colIdxs, a
+    // every call that is about to run variant 3 / 5 / 7 / 8 on CSR first verifies it on the device (one pass over colIdxs, a
     // stream synchronisation) and fails with CUSPMM_ERR_INVALID instead of computing garbage
     static const bool checkSorted = getenv("CUSPMM_CHECK_SORTED") != nullptr;
-    if (!SELL && checkSorted && (variant == 3 || variant == 5 || variant == 7) && nnz) {
+    if (!SELL && checkSorted && (variant == 3 || variant == 5 || variant == 7 || variant == 8) && nnz) {
         uint32_t bad = 0;
         const int rc = cuspmm_csr_check_sorted(rowPtrs, colIdxs, M, K, &bad, st);
         if (rc) return rc;
         if (bad)
             return set_error(CUSPMM_ERR_INVALID, "%u rows have column indices that are not strictly ascending (or >= K): the staged "
-                             "kernels (variants 3, 5, 7, hence variant 0 on this shape) need sorted rows; use variant 1, 2, 4 or 6", bad);
+                             "kernels (variants 3, 5, 7, 8, hence variant 0 on this shape) need sorted rows; use variant 1, 2, 4 or 6", bad);
     }
 
     // variants 1 and 2 keep their work decomposition but fall back to 32-bit loads when N, ldb/ldc or
@@ -720,6 +723,10 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
         if (!(vok && N % 512 == 0))
             return set_error(CUSPMM_ERR_UNSUPPORTED, "all-TMEM kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
         return spmm_rows_quad<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
+    }
+    case 8: {
+        if (SELL) return set_error(CUSPMM_ERR_UNSUPPORTED, "the tensor-core kernel (variant 8) reads CSR, not sliced ELL");
+        return spmm_csr_tc(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
     }
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);

@@ -1,0 +1,606 @@
+// spmm_csr_tc.cu -- CSR SpMM on the tensor cores (variant 8, "tensor"): tiles of A are made DENSE in shared memory on the
+// fly and multiplied with tcgen05.mma; fp32 accuracy comes from a three-product split of both operands.
+//
+// Why.  The fp32 CUDA-core kernels (variants 1-7) need one distinct element of B per FMA and are bound by the SM's operand
+// bandwidth (4.1 ms on 25605^2 x 512 at 10 %, 22 % of the FMA pipe).  A B200 tensor core does 2048 tf32 /
+// 4096 bf16 FMAs per clock and SM against 128 fp32 FMAs on the CUDA cores: from a few percent density upwards it is cheaper to
+// multiply the zeros as well.  Work is then independent of nnz:  M x K x N x (1 + 1/2 + 1/2) tensor FMAs.
+//
+// Arithmetic (what replaces the reference's fp32 multiply-add, src/spmm/csr/spmm_csr_k3.cu:30-45 / spmm_csr.cpp):
+//     a = a_t + r_a,  a_t = tf32(a) (round to nearest, 11 significant bits),  |r_a| <= 2^-11 |a|  (r_a exact in fp32)
+//     b = b_t + r_b   likewise
+//     a*b ~= a_t*b_t  (kind::tf32, exact products)  +  bf16(a)*bf16(r_b)  +  bf16(r_a)*bf16(b)   (kind::f16, bf16 operands)
+// accumulated in fp32 in tensor memory.  Dropped / perturbed terms: r_a*r_b (2^-22), bf16 rounding of the two corrections
+// (2 * 2^-11 * 2^-8): |error| <= 2^-18 |a||b| per product in the worst case (3.8e-6, inside the 1e-5 bound of the parity tests
+// for every matrix, also one-element rows), ~1e-7 of sum|a||b| on sums of random terms -- the same order as fp32 accumulation.
+//
+// Data layout.  UMMA operands are K-major without swizzle: "core matrices" of 8 rows x 16 bytes, contiguous (128 B);
+// element (row, k) of a tf32 operand lives at [k / 4][row][k % 4], of a bf16 operand at [k / 8][row][k % 8].
+//   B: a prepare kernel (one pass over B, 12 bytes per element of HBM traffic) writes, per 256-column tile ct and 16-row
+//      chunk c, one contiguous 32 KB record  [b_t: 4 x 256 x 4 fp32 | bf16(b): 2 x 256 x 8 | bf16(r_b): 2 x 256 x 8]
+//      so that a stage of B is ONE TMA bulk copy.
+//   A: a CTA owns 256 rows (two UMMA M = 128 blocks) x 256 columns of C = all 512 columns of tensor memory.  256 builder threads
+//      own one row each: per 16-column chunk they clear their row of the stage (8 x 16 B) and scatter the row's non-zeros that
+//      fall into the chunk (the rows are sorted by column: a cursor per thread; col/val arrive 4 at a time through a
+//      per-row cp.async ring in shared memory, requested a chunk ahead) as [a_t | bf16(a) | bf16(r_a)].
+//   D: TMEM columns [0, 256) = rows 0..127 of the tile, [256, 512) = rows 128..255; lane = row, column = n.
+// Per chunk and M block: 2 x tcgen05.mma kind::tf32 (M128 N256 K8) + 2 x kind::f16 (M128 N256 K16) = 1024 tensor clocks
+// per chunk against 32 KB of B from L2 (32 B/clk/SM) and ~26 non-zeros to place.
+//
+// Decomposition.  The work of a tile does not depend on its non-zeros, so tiles are spread over a persistent grid of one CTA
+// per SM: floor(tiles / grid) whole tiles per CTA (results stored directly), the remaining tiles cut into equal runs of chunks
+// ("stream-K"): a CTA that gets part of a tile's K range adds its partial sums to C (zeroed beforehand by a memset of just those
+// rows) with red.global.add.v4.f32.  A tile cut in two is deterministic (0 + x + y); more pieces (few tiles, many SMs) add in
+// arrival order.
+//
+// Warp roles (320 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = builders, later
+// the epilogue (tcgen05.ld 32x32b.x32 -> 16-byte stores / reductions).
+//
+// Semantics that differ from the sparse kernels: a zero of A is multiplied with B, so an Inf/NaN anywhere in B would poison
+// rows that never reference it.  The prepare kernel therefore raises a device flag when B holds a non-finite value (or one
+// that tf32 rounding would overflow); the tensor kernel then exits at once and the launcher's second kernel -- a plain fp32
+// warp-per-row kernel, which runs only if the flag is set -- computes C instead.  No host synchronisation either way.
+#include "tmem_common.cuh"
+
+#include <cuda_bf16.h>
+
+namespace cuspmm_b200 {
+namespace csrtc {
+
+using namespace tmemk;
+
+constexpr int kTileM = 256, kTileN = 256, kKC = 16;
+constexpr int kStages = 3;
+constexpr int kBuilders = 256, kEpilogue = 128;
+constexpr int kThreads = 64 + kBuilders + kEpilogue;
+constexpr uint32_t kABytes = 32768, kBBytes = 32768;                 // per stage
+constexpr uint32_t kOffT = 0, kOffP = 16384;                         // tf32 | bf16 pairs inside a stage of A or B
+constexpr uint32_t kPrefetchChunks = 12;                             // L2 prefetch distance of the B producer, in chunks
+constexpr uint32_t kFlushChunks = 64;                                // 256 accumulation steps between two drains of the accumulators
+constexpr uint32_t kRingOff = kStages * (kABytes + kBBytes);         // [colIdxs | vals][slot 4][row 256][16 B]
+constexpr uint32_t kRingBytes = 2 * 4 * kBuilders * 16;
+constexpr uint32_t kSmemTotal = kRingOff + kRingBytes + (3 * kStages + 2) * 8 + 16 + 128;
+static_assert(kSmemTotal <= 232448, "more than 227 KB of shared memory");
+
+struct Plan {
+    uint32_t tilesN, chunks, grid, fullWaves, remTiles;
+    uint32_t flushChunks;           // the accumulators are drained into C every so many chunks (see "Accumulation")
+    uint64_t unitsPerCta;           // chunks of the remaining tiles per CTA
+};
+
+// the segments (tile, chunk range) of CTA c, in order; every warp role walks the same sequence
+struct SegIter {
+    uint32_t i, W, G, c, chunks;
+    uint64_t u0, u1;
+    __device__ SegIter(const Plan &pl, uint32_t cta) : i(0), W(pl.fullWaves), G(pl.grid), c(cta), chunks(pl.chunks) {
+        const uint64_t total = (uint64_t)pl.remTiles * pl.chunks;
+        u0 = (uint64_t)cta * pl.unitsPerCta;
+        u1 = u0 + pl.unitsPerCta;
+        if (u0 > total) u0 = total;
+        if (u1 > total) u1 = total;
+    }
+    __device__ bool next(uint32_t &tile, uint32_t &kb, uint32_t &ke) {
+        if (i < W) { tile = c + i * G; kb = 0; ke = chunks; ++i; return true; }
+        if (u0 >= u1) return false;
+        const uint32_t t = (uint32_t)(u0 / chunks);
+        kb = (uint32_t)(u0 - (uint64_t)t * chunks);
+        const uint64_t len = (u1 - u0) < (uint64_t)(chunks - kb) ? (u1 - u0) : (uint64_t)(chunks - kb);
+        ke = kb + (uint32_t)len;
+        tile = W * G + t;
+        u0 += len;
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------- operand split
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+// v = t + r: t on the tf32 grid (never rounded up to infinity), r the exact fp32 remainder (0 for a non-finite v)
+__device__ __forceinline__ void split_tf32(float v, float &t, float &r) {
+    t = tf32_rn(v);
+    if (!(fabsf(t) < __int_as_float(0x7f800000))) t = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    r = (fabsf(v) < __int_as_float(0x7f800000)) ? v - t : 0.0f;
+}
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+    // round to nearest, but towards zero where that would leave the finite range
+    const __nv_bfloat16 h = fabsf(v) < 1.7e38f ? __float2bfloat16_rn(v) : __float2bfloat16_rz(v);
+    return __bfloat16_as_ushort(h);
+}
+
+// ---------------------------------------------------------------------------------------------- B -> tiled operand records
+// grid (2 * chunks, tilesN), 256 threads: thread = one column n, 8 consecutive k
+__global__ void __launch_bounds__(256)
+csr_tc_prepare_B(const float *__restrict__ B, uint32_t K, uint32_t N, size_t ldb, unsigned char *__restrict__ Bt, uint32_t chunks,
+                 uint32_t *__restrict__ flag) {
+    const uint32_t half = blockIdx.x & 1u, chunk = blockIdx.x >> 1, ct = blockIdx.y;
+    const uint32_t nloc = threadIdx.x, n = ct * kTileN + nloc;
+    const uint32_t k0 = blockIdx.x * 8u;
+    float b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (n < N && k0 + j < K) ? __ldcs(B + (size_t)(k0 + j) * ldb + n) : 0.0f;
+    float t[8], r[8];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        split_tf32(b[j], t[j], r[j]);
+        // non-finite, or so large that the tf32 rounding above had to be replaced by truncation
+        bad |= !(fabsf(b[j]) < 1.7e38f);
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && lane_id() == 0) atomicOr(flag, 1u);
+    unsigned char *rec = Bt + ((size_t)ct * chunks + chunk) * kBBytes;
+    float4 *pt = reinterpret_cast<float4 *>(rec + kOffT + (half * 2u) * 4096u + nloc * 16u);
+    pt[0] = make_float4(t[0], t[1], t[2], t[3]);
+    pt[256] = make_float4(t[4], t[5], t[6], t[7]);               // next k group: 256 columns x 16 B further
+    // the two correction products share ONE bf16 operand: per k the pair (bf16(r_b), bf16(b)) here against (bf16(a), bf16(r_a)) on
+    // the A side, so that a K = 16 MMA sums  bf16(a) bf16(r_b) + bf16(r_a) bf16(b)  over 8 k
+    uint4 p0, p1;
+    p0.x = bf16_bits(r[0]) | ((uint32_t)bf16_bits(b[0]) << 16);
+    p0.y = bf16_bits(r[1]) | ((uint32_t)bf16_bits(b[1]) << 16);
+    p0.z = bf16_bits(r[2]) | ((uint32_t)bf16_bits(b[2]) << 16);
+    p0.w = bf16_bits(r[3]) | ((uint32_t)bf16_bits(b[3]) << 16);
+    p1.x = bf16_bits(r[4]) | ((uint32_t)bf16_bits(b[4]) << 16);
+    p1.y = bf16_bits(r[5]) | ((uint32_t)bf16_bits(b[5]) << 16);
+    p1.z = bf16_bits(r[6]) | ((uint32_t)bf16_bits(b[6]) << 16);
+    p1.w = bf16_bits(r[7]) | ((uint32_t)bf16_bits(b[7]) << 16);
+    uint4 *pp = reinterpret_cast<uint4 *>(rec + kOffP + (half * 2u) * 4096u + nloc * 16u);
+    pp[0] = p0;
+    pp[256] = p1;
+}
+
+// ---------------------------------------------------------------------------------------------- MMA
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @ [4,6), a/b format (BF16 = 1, TF32 = 2) @ [7,10) / [10,13),
+// both operands K-major, N >> 3 @ [17,23), M >> 4 @ [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {   // always accumulates
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pick(const uint4 &v, uint32_t i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float pick(const float4 &v, uint32_t i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+// cp.async with a source size: the bytes past src_bytes are written as zeros (the tail of the arrays)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+    asm volatile("{\n\t.reg .b16 h;\n\tcvt.u16.u32 h, %1;\n\tst.shared.u16 [%0], h;\n\t}" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_zero16(uint32_t addr) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// VEC: colIdxs and vals are 16-byte aligned (blocks of 4 entries are fetched with one cp.async each)
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads, 1)
+csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
+              uint32_t M, uint32_t nnzTotal, const unsigned char *__restrict__ Bt, uint32_t N, float *__restrict__ C, size_t ldc,
+              Plan pl, const uint32_t *__restrict__ flag, int vecC) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if (*flag) return;                                        // B holds a non-finite value: the fp32 kernel that follows computes C
+    unsigned char *stA = smem;
+    unsigned char *stB = smem + kStages * kABytes;
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + kRingOff + kRingBytes);
+    uint64_t *b_full = a_full + kStages;
+    uint64_t *empty = b_full + kStages;
+    uint64_t *accum_full = empty + kStages;
+    uint64_t *accum_empty = accum_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_empty + 1);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(a_full + s, kBuilders / 32); mbar_init(b_full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(accum_full, 1);
+        mbar_init(accum_empty, kEpilogue / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    SegIter seg(pl, blockIdx.x);
+    uint32_t tile, kb, ke;
+    const uint32_t F = pl.flushChunks;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------------------- B producer
+        if (lane == 0) {
+            uint32_t s = 0, round = 0;                        // ring slot, times the ring has wrapped
+            while (seg.next(tile, kb, ke)) {
+                const uint32_t ct = tile % pl.tilesN;
+                const unsigned char *src = Bt + ((size_t)ct * pl.chunks + kb) * kBBytes;
+                for (uint32_t k = kb; k < ke; ++k, src += kBBytes) {
+                    // the records of the next chunks are pulled into L2 well ahead: a stage is refilled only two chunks (~2000
+                    // clocks) before it is consumed, enough for an L2 hit but not for a miss to HBM
+                    if (k + kPrefetchChunks < pl.chunks)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)kPrefetchChunks * kBBytes), "r"(kBBytes) : "memory");
+                    if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+                    mbar_expect_tx(b_full + s, kBBytes);
+                    bulk_g2s(stB + s * kBBytes, src, kBBytes, b_full + s);
+                    if (++s == kStages) { s = 0; ++round; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idT = make_idesc(2, 128, kTileN), idH = make_idesc(1, 128, kTileN);
+            uint32_t s = 0, round = 0, pieces = 0;
+#ifdef CUSPMM_TC_DEBUG
+            long long dbgA = 0, dbgB = 0, dbgE = 0, dbgN = 0;
+            const long long dbgT0 = clock64();
+#endif
+            while (seg.next(tile, kb, ke)) {
+                for (uint32_t k = kb; k < ke; ++k) {
+                    const bool first = (k - kb) % F == 0;     // first chunk of a piece: the accumulators start over
+#ifdef CUSPMM_TC_DEBUG
+                    const long long te = clock64();
+#endif
+                    if (first && pieces > 0) { mbar_wait(accum_empty, (pieces - 1) & 1); tc_fence_after(); }
+#ifdef CUSPMM_TC_DEBUG
+                    dbgE += clock64() - te;
+#endif
+#ifdef CUSPMM_TC_DEBUG
+                    const long long t0 = clock64();
+                    mbar_wait(a_full + s, round & 1);
+                    const long long t1 = clock64();
+                    mbar_wait(b_full + s, round & 1);
+                    const long long t2 = clock64();
+                    dbgA += t1 - t0; dbgB += t2 - t1; ++dbgN;
+#else
+                    mbar_wait(a_full + s, round & 1);
+                    mbar_wait(b_full + s, round & 1);
+#endif
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(stA + s * kABytes), b0 = smem_u32(stB + s * kBBytes);
+                    // B operand (N = 256 columns of the tile): next k group 4096 B, next 8 columns 128 B.  k groups 0..3 of a tile
+                    // hold 4 k each: a tf32 MMA (K = 8) and a pair MMA (K = 16 = 8 k x 2) both take two of them
+                    const uint64_t bT0 = make_desc(b0 + kOffT, 4096, 128), bT1 = make_desc(b0 + kOffT + 8192, 4096, 128);
+                    const uint64_t bP0 = make_desc(b0 + kOffP, 4096, 128), bP1 = make_desc(b0 + kOffP + 8192, 4096, 128);
+#pragma unroll
+                    for (uint32_t m = 0; m < 2; ++m) {
+                        // A operand (M = 128 rows): next k group 2048 B, next 8 rows 128 B
+                        const uint32_t d = tmem_base + m * kTileN;
+                        const uint32_t am = a0 + m * 8192;
+                        umma_tf32(d, make_desc(am + kOffT, 2048, 128), bT0, idT, first ? 0u : 1u);
+                        umma_tf32(d, make_desc(am + kOffT + 4096, 2048, 128), bT1, idT, 1u);
+                        umma_bf16(d, make_desc(am + kOffP, 2048, 128), bP0, idH);         // bf16(a) x bf16(r_b) + bf16(r_a) x bf16(b), k 0..7
+                        umma_bf16(d, make_desc(am + kOffP + 4096, 2048, 128), bP1, idH);  // k 8..15
+                    }
+                    tc_commit(empty + s);                     // the stage may be rebuilt once these MMAs have read it
+                    if (++s == kStages) { s = 0; ++round; }
+                    if ((k + 1 - kb) % F == 0 || k + 1 == ke) { tc_commit(accum_full); ++pieces; }
+                }
+            }
+#ifdef CUSPMM_TC_DEBUG
+            if (blockIdx.x == 0 || blockIdx.x == 77)
+                printf("cta %u: chunks %lld, total %lld clk (%lld per chunk); issuer waited: A %lld, B %lld, drain %lld per chunk\n", blockIdx.x, dbgN,
+                       clock64() - dbgT0, (clock64() - dbgT0) / dbgN, dbgA / dbgN, dbgB / dbgN, dbgE / dbgN);
+#endif
+        }
+    } else if (warp < 2 + kBuilders / 32) {
+        // ---------------------------------------------------------------------------- builders
+        const uint32_t t = threadIdx.x - 64;                  // row of the tile this thread builds
+        const uint32_t mblk = t >> 7, rowInBlk = t & 127;
+        const uint32_t offT = kOffT + mblk * 8192 + rowInBlk * 16;
+        const uint32_t ring = smem_u32(smem + kRingOff) + t * 16u;       // this row's slot 0 of the colIdxs ring; vals 16 KB further
+        const uint32_t stA32 = smem_u32(stA);
+        uint32_t s = 0, round = 0;
+        while (seg.next(tile, kb, ke)) {
+            const uint32_t r = (tile / pl.tilesN) * kTileM + t;
+            uint32_t p = 0, end = 0;
+            if (r < M) {
+                p = __ldg(rowPtrs + r);
+                end = __ldg(rowPtrs + r + 1);
+                if (kb > 0) {                                 // first entry of the row at or after column 16 kb
+                    const uint32_t target = kb * kKC;
+                    uint32_t lo = p, hi = end;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(colIdxs + mid) < target) lo = mid + 1; else hi = mid;
+                    }
+                    p = lo;
+                }
+            }
+            // Entries reach the thread through a ring in shared memory: 4 slots of 4 entries (16 B of colIdxs + 16 B of vals) per
+            // row, filled with cp.async.  (A register FIFO filled with ordinary loads does not work here: the scoreboard is
+            // per warp and register, so a lane shifting its FIFO waits for the load another lane issued a moment ago -- ncu on the
+            // first version: 29 % of all samples on that move, one exposed memory latency per chunk.)  Refills are issued at the
+            // start of a chunk, one commit group per chunk, and cp.async.wait_group 2 makes the groups older than two chunks
+            // visible (waiting for the group of the previous chunk exposed the memory latency of every chunk: 2.1 ms at 2 % density
+            // where the tensor pipe needs 1.3): a block is requested 12..16 entries before it is read.  Entry p of the row lives at
+            // ring + (p / 4 % 4) * 4096 + (p % 4) * 4.
+            uint32_t fb = p & ~3u;                            // next block to request
+            uint32_t lb = fb;                                 // entries below lb have landed
+            auto refill = [&]() {
+                uint32_t lim = (p & ~3u) + 16u;
+                if (lim > end) lim = end;
+                while (fb < lim) {
+                    const uint32_t dst = ring + ((fb & 12u) << 10);
+                    if (VEC) {
+                        const uint32_t valid = (nnzTotal - fb < 4u ? nnzTotal - fb : 4u) * 4u;
+                        cp_async16(dst, colIdxs + fb, valid);
+                        cp_async16(dst + 16384u, vals + fb, valid);
+                    } else {
+#pragma unroll
+                        for (uint32_t e = 0; e < 4; ++e) {
+                            const bool in = fb + e < nnzTotal;
+                            cp_async4(dst + 4 * e, colIdxs + (in ? fb + e : fb), in ? 4u : 0u);
+                            cp_async4(dst + 16384u + 4 * e, vals + (in ? fb + e : fb), in ? 4u : 0u);
+                        }
+                    }
+                    fb += 4;
+                }
+            };
+
+            uint32_t fbPrev = fb;                             // fb before the refill of the previous chunk
+            for (uint32_t k = kb; k < ke; ++k) {
+                const uint32_t fbBefore = fb;
+                refill();
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (k == kb) { asm volatile("cp.async.wait_group 0;" ::: "memory"); lb = fb; }
+                else {                                        // all groups but the last two have landed: requested >= 2 chunks ago
+                    asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    if (fbPrev > lb) lb = fbPrev;
+                }
+                fbPrev = fbBefore;
+                if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+                const uint32_t a = stA32 + s * kABytes;
+                const uint32_t aT = a + offT;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) { sts_zero16(aT + g * 2048); sts_zero16(aT + kOffP + g * 2048); }
+                const uint32_t k0 = k * kKC;
+                for (;;) {
+                    const uint32_t stop = end < lb ? end : lb;
+                    bool done = false;
+                    while (p < stop) {
+                        const uint32_t ea = ring + ((p & 12u) << 10) + ((p & 3u) << 2);
+                        const uint32_t kk = lds_u32(ea) - k0;                    // columns ascend and are >= k0 here
+                        if (kk >= (uint32_t)kKC) { done = true; break; }
+                        const float v = __uint_as_float(lds_u32(ea + 16384u));
+                        const uint32_t bits = __float_as_uint(v);
+                        uint32_t tb = (bits + 0x1000u) & 0xFFFFE000u;          // tf32, round to nearest (ties away)
+                        float res = v - __uint_as_float(tb);                   // exact
+                        uint32_t pk;                                            // low half bf16(v), high half bf16(res)
+                        if ((bits << 1) >= 0xFE000000u) {                      // |v| >= 2^127, Inf, NaN: truncate, no remainder for Inf / NaN
+                            tb = bits & 0xFFFFE000u;
+                            res = (bits << 1) < 0xFF000000u ? v - __uint_as_float(tb) : 0.0f;
+                            pk = (bits >> 16) | ((uint32_t)bf16_bits(res) << 16);
+                        } else {
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(res), "f"(v));
+                        }
+                        // tf32 tile and pair tile have the same geometry (4 k per 16-byte core-matrix row), 16 KB apart
+                        const uint32_t dstT = aT + ((kk & 12u) << 9) + ((kk & 3u) << 2);
+                        sts_u32(dstT, tb);
+                        sts_u32(dstT + kOffP, pk);
+                        ++p;
+                    }
+                    if (done || p >= end) break;
+                    // the row has more entries, but they are not known to have landed (a chunk that used more than ~2 blocks)
+                    if (p >= fb) { refill(); asm volatile("cp.async.commit_group;" ::: "memory"); }
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    lb = fb;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core (async proxy) reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + s);
+                if (++s == kStages) { s = 0; ++round; }
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------------------- epilogue (warps 10..13)
+        // TMEM lanes [32 q, 32 q + 32) are the ones this warp may read; it drains both M blocks of those lanes.  Every piece is
+        // added to C (zeroed by the launcher) with red.global.add.v4.f32; a tile that is one single piece is stored.
+        // (Load-add-store by the CTA that owns a tile was 3x slower than red.add: the C tile does not stay in L2 between two
+        //  drains and the loads are serialised behind the TMEM reads -- 59 000 clocks per drain against 18 000.)
+        const uint32_t q = warp & 3;
+        uint32_t pieces = 0;
+        while (seg.next(tile, kb, ke)) {
+            const uint32_t rt = tile / pl.tilesN, ct = tile % pl.tilesN;
+            const bool direct = (kb == 0 && ke == pl.chunks && pl.chunks <= F);     // the only piece of the tile: plain stores
+            const uint32_t ncols = N - ct * kTileN < (uint32_t)kTileN ? N - ct * kTileN : (uint32_t)kTileN;
+            for (uint32_t k = kb; k < ke; k += F, ++pieces) {
+                mbar_wait(accum_full, pieces & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (uint32_t em = 0; em < 2; ++em) {
+                    const uint32_t er = rt * kTileM + em * 128 + q * 32 + lane;
+                    float *crow = C + (size_t)er * ldc + (size_t)ct * kTileN;
+#pragma unroll 1
+                    for (uint32_t cb = 0; cb < kTileN / 32; ++cb) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + em * kTileN + cb * 32;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                                     "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                     : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (er < M) {
+                            const uint32_t c0 = cb * 32;
+                            if (vecC) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    if (c0 + 4 * j + 4 <= ncols) {
+                                        float *dst = crow + c0 + 4 * j;
+                                        const float x = __uint_as_float(v[4 * j]), y = __uint_as_float(v[4 * j + 1]),
+                                                    z2 = __uint_as_float(v[4 * j + 2]), w = __uint_as_float(v[4 * j + 3]);
+                                        if (direct) __stcs(reinterpret_cast<float4 *>(dst), make_float4(x, y, z2, w));
+                                        else red_add_v4(dst, x, y, z2, w);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if (c0 + j < ncols) {
+                                        if (direct) crow[c0 + j] = __uint_as_float(v[j]);
+                                        else atomicAdd(crow + c0 + j, __uint_as_float(v[j]));
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(accum_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+} // namespace csrtc
+
+// The kernel that computes C when B holds non-finite values (it exits at once otherwise): plain fp32, a warp per row, lanes over
+// the columns.  Only stored entries are multiplied, as in the reference; speed does not matter here.
+__global__ void __launch_bounds__(256)
+csr_tc_fallback_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
+                       uint32_t M, const float *__restrict__ B, uint32_t N, size_t ldb, float *__restrict__ C, size_t ldc,
+                       const uint32_t *__restrict__ onlyIf) {
+    if (!*onlyIf) return;
+    const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += warpsPerGrid) {
+        const uint32_t p0 = rowPtrs[r], p1 = rowPtrs[r + 1];
+        for (uint32_t n0 = 0; n0 < N; n0 += 128) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            for (uint32_t p = p0; p < p1; ++p) {
+                const float a = vals[p];
+                const float *brow = B + (size_t)colIdxs[p] * ldb + n0 + lane_id();
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + 32 * j + lane_id() < N) acc[j] = fmaf(a, brow[32 * j], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (n0 + 32 * j + lane_id() < N) C[(size_t)r * ldc + n0 + 32 * j + lane_id()] = acc[j];
+        }
+    }
+}
+
+// one memory pool per device for the tiled copy of B: stream-ordered (cudaMallocAsync / cudaFreeAsync on the caller's stream), so
+// concurrent calls on different streams never share a buffer and nothing synchronises; the pool keeps what it has allocated
+static cudaMemPool_t tc_pool(int dev) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64) return nullptr;
+    if (!pools[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) != cudaSuccess) { pools[dev] = nullptr; return nullptr; }
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    return pools[dev];
+}
+
+size_t csr_tc_workspace_bytes(uint32_t K, uint32_t N) {
+    const uint64_t tilesN = (N + csrtc::kTileN - 1) / csrtc::kTileN, chunks = (K + csrtc::kKC - 1) / csrtc::kKC;
+    return (size_t)(tilesN * chunks * csrtc::kBBytes + 256);
+}
+
+// variant 8 of the CSR kernels.  Rows must be sorted by column (as for variants 3, 5, 7).
+int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
+                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+    using namespace csrtc;
+    if (K == 0) {
+        CUSPMM_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+        return CUSPMM_OK;
+    }
+    int dev = 0;
+    CUSPMM_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool = tc_pool(dev);
+    if (!pool) return set_error(CUSPMM_ERR_CUDA, "no memory pool for the tiled copy of B on device %d", dev);
+
+    Plan pl;
+    pl.tilesN = (N + kTileN - 1) / kTileN;
+    pl.chunks = (K + kKC - 1) / kKC;
+    const uint32_t tilesM = (M + kTileM - 1) / kTileM;
+    const uint64_t tiles = (uint64_t)tilesM * pl.tilesN;
+    const uint64_t units = tiles * pl.chunks;
+    // one CTA per SM; with little work, at least 8 chunks per CTA
+    uint64_t grid = (uint64_t)sm_count();
+    if (units / 8 < grid) grid = units / 8 ? units / 8 : 1;
+    pl.grid = (uint32_t)grid;
+    pl.fullWaves = (uint32_t)(tiles / grid);
+    pl.remTiles = (uint32_t)(tiles - (uint64_t)pl.fullWaves * grid);
+    pl.unitsPerCta = ((uint64_t)pl.remTiles * pl.chunks + grid - 1) / grid;
+    static const int flushEnv = getenv("CUSPMM_TC_FLUSH") ? atoi(getenv("CUSPMM_TC_FLUSH")) : 0;      // tuning hook
+    pl.flushChunks = flushEnv > 0 ? (uint32_t)flushEnv : kFlushChunks;
+
+    const size_t bytes = csr_tc_workspace_bytes(K, N);
+    unsigned char *ws = nullptr;
+    CUSPMM_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), bytes, pool, st));
+    uint32_t *flag = reinterpret_cast<uint32_t *>(ws + bytes - 256);
+    int rc = CUSPMM_OK;
+    do {
+        if (cudaMemsetAsync(flag, 0, sizeof(uint32_t), st) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "memset of the flag failed"); break; }
+        csr_tc_prepare_B<<<dim3(2 * pl.chunks, pl.tilesN), 256, 0, st>>>(B, K, N, ldb, ws, pl.chunks, flag);
+        if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_prepare_B failed"); break; }
+        count_launch();
+        // every tile is drained into C piece by piece with red.add (only a tile that is a single piece is stored): C starts at zero
+        const bool allDirect = pl.chunks <= pl.flushChunks && (pl.remTiles == 0 || pl.unitsPerCta % pl.chunks == 0);
+        if (!allDirect && cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st) != cudaSuccess) {
+            rc = set_error(CUSPMM_ERR_CUDA, "memset of C failed");
+            break;
+        }
+        const bool vecA = ((reinterpret_cast<uintptr_t>(colIdxs) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
+        const int vecC = (N % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        auto kern = vecA ? csr_tc_kernel<true> : csr_tc_kernel<false>;
+        if (set_smem_once(kern, kSmemTotal) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "cannot reserve %u bytes of shared memory", kSmemTotal); break; }
+        kern<<<pl.grid, kThreads, kSmemTotal, st>>>(rowPtrs, colIdxs, vals, M, nnz, ws, N, C, ldc, pl, flag, vecC);
+        if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_kernel failed: %s", cudaGetErrorString(cudaPeekAtLastError())); break; }
+        count_launch();
+        csr_tc_fallback_kernel<<<(unsigned)sm_count() * 4, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc, flag);
+        if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_fallback_kernel failed"); break; }
+        count_launch();
+    } while (0);
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+} // namespace cuspmm_b200

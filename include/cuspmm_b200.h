@@ -70,14 +70,22 @@ int cuspmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
  *   7  every B read from tensor memory: TMA -> shared-memory ring -> tcgen05.cp.128x256b -> a 128-row TMEM ring of B; a warp
  *      owns 8 rows x the 128 columns of its TMEM lane quarter and fetches B with tcgen05.ld.x4 (no shared-memory operand
  *      reads at all); fp32 FMA in CSR order like 1..5 (N % 512 == 0, else CUSPMM_ERR_UNSUPPORTED)
+ *   8  tensor cores: 256-row x 16-column tiles of A are made dense in shared memory and multiplied with tcgen05.mma against a
+ *      pre-tiled copy of B (built per call, in a stream-ordered pool allocation of 8 bytes per element of B).  fp32-grade
+ *      result from a three-product split: tf32(a)*tf32(b) + bf16(a)*bf16(b - tf32(b)) + bf16(a - tf32(a))*bf16(b), fp32
+ *      accumulation in tensor memory; per-product error <= 2^-18 |a||b| (3.8e-6) in the worst case, ~1e-7 of sum|a||b| on
+ *      sums.  Work does not depend on nnz (M*K*N*2 tensor FMAs): it wins from a few percent density upwards.  Any N.  If B holds
+ *      a non-finite value (a dense product would spread it to rows that never reference it) a device-side flag reroutes the
+ *      call to a plain fp32 kernel without host synchronisation.  Tiles cut along K add their partial sums with red.add:
+ *      bit-reproducible as long as no tile is cut into more than two pieces (always the case when tiles >= SMs).
  *
- * PRECONDITION for variants 0, 3, 5, 7 (and everything built on them: COO variant 2, sliced ELL, the host-buffer and multi-GPU
+ * PRECONDITION for variants 0, 3, 5, 7, 8 (and everything built on them: COO variant 2, sliced ELL, the host-buffer and multi-GPU
  * entry points): column indices ascend strictly inside every row, as the reference's converter writes them
  * (convert_mtx.py:127-143, scipy CSR with sorted indices).  Variants 1, 2, 4, 6 accept any order.  cuspmm_csr_check_sorted
  * verifies it on the device; with the environment variable CUSPMM_CHECK_SORTED set, every CSR call that is about to run a
  * staged kernel performs that check first and fails with CUSPMM_ERR_INVALID on unsorted rows (a debug guard: it costs a pass
  * over colIdxs and a stream synchronisation). */
-#define CUSPMM_CSR_NUM_VARIANTS 7
+#define CUSPMM_CSR_NUM_VARIANTS 8
 int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
                     uint32_t M, uint32_t K, uint32_t nnz,
                     const float *B_dev, uint32_t N, size_t ldb,
