@@ -10,31 +10,45 @@
 //     a = a_t + r_a,  a_t = tf32(a) (round to nearest, 11 significant bits),  |r_a| <= 2^-11 |a|  (r_a exact in fp32)
 //     b = b_t + r_b   likewise
 //     a*b ~= a_t*b_t  (kind::tf32, exact products)  +  bf16(a)*bf16(r_b)  +  bf16(r_a)*bf16(b)   (kind::f16, bf16 operands)
-// accumulated in fp32 in tensor memory.  Dropped / perturbed terms: r_a*r_b (2^-22), bf16 rounding of the two corrections
-// (2 * 2^-11 * 2^-8): |error| <= 2^-18 |a||b| per product in the worst case (3.8e-6, inside the 1e-5 bound of the parity tests
-// for every matrix, also one-element rows), ~1e-7 of sum|a||b| on sums of random terms -- the same order as fp32 accumulation.
+// accumulated in fp32 in tensor memory.  Dropped / perturbed terms: r_a*r_b (2^-22) and the bf16 rounding (2^-8) of the factor
+// that multiplies a remainder (2^-11) in each of the two corrections: |error| <= 2^-17 |a||b| per product in the worst case
+// (7.6e-6; observed maximum over 10^6 one-entry rows 4.4e-6), inside the 1e-5 bound of the parity tests for every matrix;
+// on sums of many terms the errors average out: ~5e-7 of sum|a||b| at 25605^2, the same order as fp32 accumulation.
+//
+// Accumulation.  tcgen05.mma does not round its fp32 accumulator to nearest: it truncates.  Every MMA step loses on average
+// 2^-25.5 of |accumulator| TOWARDS ZERO -- a bias, not noise: after the 6400 steps of K = 25605 the first version was 1.2e-5
+// of sum|a||b| off (7.7e-3 absolute on |C| ~ 20), outside the tolerance.  So the accumulators are drained into C every
+// kFlushChunks = 64 chunks (256 steps: bias <= 5e-6 of |partial sum| even when all terms have one sign) with
+// red.global.add.v4.f32, whose additions round to nearest, and start over from zero.  A drain costs ~18 000 clocks (the LSU
+// retires about one reduction lane per 1.3 clocks): +12 % at 64 chunks.
 //
 // Data layout.  UMMA operands are K-major without swizzle: "core matrices" of 8 rows x 16 bytes, contiguous (128 B);
 // element (row, k) of a tf32 operand lives at [k / 4][row][k % 4], of a bf16 operand at [k / 8][row][k % 8].
+//   The two correction products share ONE bf16 operand of interleaved pairs: per k the A side holds (bf16(a), bf16(r_a)), the
+//   B side (bf16(r_b), bf16(b)), so a K = 16 MMA sums both corrections over 8 k -- and the pair of an entry is one 32-bit store.
 //   B: a prepare kernel (one pass over B, 12 bytes per element of HBM traffic) writes, per 256-column tile ct and 16-row
-//      chunk c, one contiguous 32 KB record  [b_t: 4 x 256 x 4 fp32 | bf16(b): 2 x 256 x 8 | bf16(r_b): 2 x 256 x 8]
+//      chunk c, one contiguous 32 KB record  [b_t: 4 k-groups x 256 columns x 4 fp32 | pairs: 4 k-groups x 256 x 4 pairs]
 //      so that a stage of B is ONE TMA bulk copy.
 //   A: a CTA owns 256 rows (two UMMA M = 128 blocks) x 256 columns of C = all 512 columns of tensor memory.  256 builder threads
 //      own one row each: per 16-column chunk they clear their row of the stage (8 x 16 B) and scatter the row's non-zeros that
 //      fall into the chunk (the rows are sorted by column: a cursor per thread; col/val arrive 4 at a time through a
-//      per-row cp.async ring in shared memory, requested a chunk ahead) as [a_t | bf16(a) | bf16(r_a)].
+//      per-row cp.async ring in shared memory, requested chunks ahead) as [a_t | pair], two 32-bit stores 16 KB apart.
 //   D: TMEM columns [0, 256) = rows 0..127 of the tile, [256, 512) = rows 128..255; lane = row, column = n.
 // Per chunk and M block: 2 x tcgen05.mma kind::tf32 (M128 N256 K8) + 2 x kind::f16 (M128 N256 K16) = 1024 tensor clocks
-// per chunk against 32 KB of B from L2 (32 B/clk/SM) and ~26 non-zeros to place.
+// per chunk against 32 KB of B from L2 (32 B/clk/SM) and ~410 non-zeros to place (10 % density).
+//
+// What bounds it (measured, 25605^2 x 512; clock64 around the issuer's waits, profiles/r02_tc_*): shared-memory bandwidth.
+// The MMAs of a chunk read 96 KB of operands (B twice, once per M block: 768 clocks of the 128 B/clk pipe), TMA writes 32 KB,
+// the builders clear 32 KB and scatter: ~1500 clocks per chunk with no non-zeros at all, 2050 at 10 % (the scattered 4-byte
+// stores, 16 bytes apart per row, cost ~540 of them).  The tensor pipe itself needs ~1160.
 //
 // Decomposition.  The work of a tile does not depend on its non-zeros, so tiles are spread over a persistent grid of one CTA
-// per SM: floor(tiles / grid) whole tiles per CTA (results stored directly), the remaining tiles cut into equal runs of chunks
-// ("stream-K"): a CTA that gets part of a tile's K range adds its partial sums to C (zeroed beforehand by a memset of just those
-// rows) with red.global.add.v4.f32.  A tile cut in two is deterministic (0 + x + y); more pieces (few tiles, many SMs) add in
-// arrival order.
+// per SM: floor(tiles / grid) whole tiles per CTA, the remaining tiles cut into equal runs of chunks ("stream-K").  All pieces
+// (drains of one CTA, partial tiles of several) meet in C through red.add on a zeroed C; the pieces of one CTA arrive in
+// program order, those of two CTAs that share a tile in arrival order (run-to-run differences in the last bits of those tiles).
 //
-// Warp roles (320 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = builders, later
-// the epilogue (tcgen05.ld 32x32b.x32 -> 16-byte stores / reductions).
+// Warp roles (448 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = builders,
+// warps 10..13 = epilogue (tcgen05.ld 32x32b.x32 -> 16-byte reductions / stores).
 //
 // Semantics that differ from the sparse kernels: a zero of A is multiplied with B, so an Inf/NaN anywhere in B would poison
 // rows that never reference it.  The prepare kernel therefore raises a device flag when B holds a non-finite value (or one
@@ -394,10 +408,15 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                         uint32_t tb = (bits + 0x1000u) & 0xFFFFE000u;          // tf32, round to nearest (ties away)
                         float res = v - __uint_as_float(tb);                   // exact
                         uint32_t pk;                                            // low half bf16(v), high half bf16(res)
-                        if ((bits << 1) >= 0xFE000000u) {                      // |v| >= 2^127, Inf, NaN: truncate, no remainder for Inf / NaN
-                            tb = bits & 0xFFFFE000u;
-                            res = (bits << 1) < 0xFF000000u ? v - __uint_as_float(tb) : 0.0f;
-                            pk = (bits >> 16) | ((uint32_t)bf16_bits(res) << 16);
+                        if ((bits << 1) >= 0xFE000000u) {                      // |v| >= 2^127, Inf, NaN
+                            if ((bits << 1) < 0xFF000000u) {                   // finite: truncate instead of rounding up to infinity
+                                tb = bits & 0xFFFFE000u;
+                                res = v - __uint_as_float(tb);
+                                pk = (bits >> 16) | ((uint32_t)bf16_bits(res) << 16);
+                            } else {                                            // Inf / NaN: main product only (Inf - Inf in the corrections
+                                tb = (bits & 0x007FFFFFu) ? (bits | 0x00400000u) & 0xFFFFE000u : bits;   //  would turn Inf into NaN)
+                                pk = 0u;
+                            }
                         } else {
                             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(res), "f"(v));
                         }

@@ -33,6 +33,9 @@ DenseMatrix<DT, MT> *spmmCSRWrapper6(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT,
 // additive: every B read from tensor memory (columns split over the TMEM lane quarters)
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmCSRWrapper7(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+// additive: tensor cores -- tiles of A made dense in shared memory, tcgen05.mma with a tf32 + bf16 three-product split
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmCSRWrapper8(SparseMatrixCSR<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 
 template <typename DT, typename MT, typename AccT>
 class EngineCSR : public EngineBase {
@@ -46,7 +49,7 @@ class EngineCSR : public EngineBase {
     double seqTime = 1.f;
 
     explicit EngineCSR(std::string dirPath) {
-        this->numKernels = CUSPMM_CSR_NUM_VARIANTS;   // 7: the reference's four slots + the three additive kernels
+        this->numKernels = CUSPMM_CSR_NUM_VARIANTS;   // 8: the reference's four slots + the four additive kernels
         this->dirPath = dirPath;
         this->fmt = "CSR";
     }
@@ -69,6 +72,7 @@ class EngineCSR : public EngineBase {
         if (num == 5) return spmmCSRWrapper5<DT, MT, AccT>(ma, mb, mc);
         if (num == 6) return spmmCSRWrapper6<DT, MT, AccT>(ma, mb, mc);
         if (num == 7) return spmmCSRWrapper7<DT, MT, AccT>(ma, mb, mc);
+        if (num == 8) return spmmCSRWrapper8<DT, MT, AccT>(ma, mb, mc);
         if (num == -1) return spmmCSRWrapper3<DT, MT, AccT>(ma, mb, mc);
         throw std::runtime_error("Not implemented");
     }

@@ -209,6 +209,7 @@ CSR_WRAPPER(4, "csr_rowsplit_scalar")
 CSR_WRAPPER(5, "csr_staged_tma_tmem")
 CSR_WRAPPER(6, "csr_nnz_split_ordered_carry")
 CSR_WRAPPER(7, "csr_all_tmem_quad")
+CSR_WRAPPER(8, "csr_tensor_split")
 
 // ------------------------------------------------------------------------------- COO wrappers
 template <typename DT, typename MT, typename AccT>
@@ -358,6 +359,7 @@ template Dn *spmmCSRWrapper4<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper5<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper6<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCSRWrapper7<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
+template Dn *spmmCSRWrapper8<F, U, A>(SparseMatrixCSR<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper1<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmCOOWrapper2<F, U, A>(SparseMatrixCOO<F, U> *, Dn *, Dn *);
 template Dn *spmmELLWrapper1<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);

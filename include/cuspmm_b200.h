@@ -73,11 +73,12 @@ int cuspmm_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
  *   8  tensor cores: 256-row x 16-column tiles of A are made dense in shared memory and multiplied with tcgen05.mma against a
  *      pre-tiled copy of B (built per call, in a stream-ordered pool allocation of 8 bytes per element of B).  fp32-grade
  *      result from a three-product split: tf32(a)*tf32(b) + bf16(a)*bf16(b - tf32(b)) + bf16(a - tf32(a))*bf16(b), fp32
- *      accumulation in tensor memory; per-product error <= 2^-18 |a||b| (3.8e-6) in the worst case, ~1e-7 of sum|a||b| on
- *      sums.  Work does not depend on nnz (M*K*N*2 tensor FMAs): it wins from a few percent density upwards.  Any N.  If B holds
+ *      accumulation in tensor memory, drained into C (round-to-nearest adds) every 64 chunks of 16 columns of A because
+ *      the tensor core truncates when it accumulates; per-product error <= 2^-17 |a||b| (7.6e-6) in the worst case, ~5e-7
+ *      of sum|a||b| on long sums.  Work does not depend on nnz (M*K*N*2 tensor FMAs): it wins from a few percent density upwards.  Any N.  If B holds
  *      a non-finite value (a dense product would spread it to rows that never reference it) a device-side flag reroutes the
- *      call to a plain fp32 kernel without host synchronisation.  Tiles cut along K add their partial sums with red.add:
- *      bit-reproducible as long as no tile is cut into more than two pieces (always the case when tiles >= SMs).
+ *      call to a plain fp32 kernel without host synchronisation.  Partial sums meet in C through red.add: tiles that
+ *      two CTAs share (the last tiles of a grid that is not a multiple of the SM count) differ run to run in the last bits.
  *
  * PRECONDITION for variants 0, 3, 5, 7, 8 (and everything built on them: COO variant 2, sliced ELL, the host-buffer and multi-GPU
  * entry points): column indices ascend strictly inside every row, as the reference's converter writes them

@@ -72,9 +72,9 @@ def test_cli_all_formats_on_reference_fixtures(case):
     for r in recs:
         by_fmt.setdefault(r["format"], []).append(r)
     assert set(by_fmt) == {"CSR", "COO", "BSR", "ELL"}
-    # CSR: kernel 0 (CPU), 1..4 as the reference numbers them + 5 (dual-path staged), 6 (nnz split), 7 (all-TMEM), cuSPARSE (-1)
+    # CSR: kernel 0 (CPU), 1..4 as the reference numbers them + 5 (dual-path staged), 6 (nnz split), 7 (all-TMEM), 8 (tensor cores), cuSPARSE (-1)
     kinds = [r["kernelType"] for r in by_fmt["CSR"]]
-    assert kinds == ["0", "1", "2", "3", "4", "5", "6", "7", "-1"]
+    assert kinds == ["0", "1", "2", "3", "4", "5", "6", "7", "8", "-1"]
     n_cols = int(open(os.path.join(d, "dense.in")).readline().split()[1])
     for r in recs:
         k, fmt = r["kernelType"], r["format"]
@@ -140,7 +140,7 @@ def test_cli_on_generated_directory(tmp_path):
     subprocess.run(["python", os.path.join(ROOT, "scripts", "gen_data.py"), d, "--rows", "1024", "--cols", "768", "--density", "0.1",
                     "--N", "512", "--range", "-1", "1", "--bsr-block", "16"], check=True, capture_output=True)
     recs = records(run("--csr", "--coo", "--ell", "--bsr", "-d", d, "--iters", "2").stdout)
-    assert len(recs) == 9 + 4 + 6 + 4          # CSR 0..7 + cuSPARSE, COO 0..2 + cuSPARSE, ELL 0..5, BSR 0..3
+    assert len(recs) == 10 + 4 + 6 + 4         # CSR 0..8 + cuSPARSE, COO 0..2 + cuSPARSE, ELL 0..5, BSR 0..3
     for r in recs:
         if r["format"] == "BSR" and r["kernelType"] in ("2", "3"):
             # bf16/fp16 operand rounding (2^-9 / 2^-12 per operand) is judged with its own tolerance in
