@@ -261,6 +261,27 @@ def roofline_record(pk, alg_bytes, ms, flops, nnz, N, sm_mhz=None, traffic=None)
             "binding": max((("hbm", t_hbm), ("fp32_fma", t_fp32), ("smem_operand_bw", t_l1)), key=lambda x: x[1])[0]}
 
 
+def tensor_roofline_record(pk, M, K, N, alg_bytes, ms, nnz, sm_mhz=None, traffic=None):
+    """CSR variant 8 (spmm_csr_tc.cu): the kernel multiplies DENSE tiles, so its roofline is the tensor pipe.  Executed work per
+    launch: Mpad x Kpad x Npad MACs in tf32 (half the bf16 rate) + the same MACs twice over in bf16 (the pair product has K
+    doubled); in bf16-equivalent flops that is 8 x Mpad x Kpad x Npad.  peak = the measured dense bf16 rate."""
+    Mp, Kp, Np = -(-M // 512) * 512, -(-K // 16) * 16, -(-N // 256) * 256
+    macs = float(Mp) * Kp * Np
+    achieved = 8.0 * macs / (ms * 1e-3) / 1e12
+    clk = sm_mhz or 1965.0
+    t_tensor = 8.0 * macs / (pk["bf16"] * 1e12) * 1e3
+    t_hbm = alg_bytes / (pk["hbm"] * 1e9) * 1e3
+    useful = 2.0 * nnz * N / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
+            "traffic": traffic, "peak_source": pk["bf16_src"], "kernel_ms": ms,
+            "executed_macs_per_launch": macs, "padded_shape": [Mp, Kp, Np],
+            "unit_note": "bf16-equivalent executed TFLOP/s: 2 flop x (tf32 MACs x 2 + bf16 MACs), zeros and padding included",
+            "useful_tflops": useful, "useful_frac_of_fp32_fma_peak": useful / (148 * 128 * 2 * clk * 1e6 / 1e12),
+            "hbm_view": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_GBs": alg_bytes / (ms * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm"], "peak_source": pk["hbm_src"]},
+            "bounds_ms": {"tensor": t_tensor, "hbm": t_hbm}, "binding": "tensor"}
+
+
 def lookup_traffic(workload, fmt, kernel):
     """DRAM bytes of one launch from the committed ncu --set full capture -- only when that capture was taken on the SAME
     kernel the selector launches now (the file records the kernel per entry); otherwise null rather than a stale number."""
@@ -703,21 +724,58 @@ def main():
         except Exception as ex:
             cusparse = {"error": str(ex)[:200]}
 
+    # ---- the fp32 FMA kernels on the same panels (tensor mode off), when the selector chose the tensor-core kernel
+    fp32_path = None
+    if fmt == "csr" and kernel_name == "csr_tensor" and not args.variant:
+        prev = b.set_csr_tensor_mode(0)
+        try:
+            kv = b.csr_selected_variant(Ml, K, nnz, N)
+            tmp = torch.empty_like(Cd)
+            run32 = lambda: b.spmm_csr(rp_l, ci_l, va_l, Ml, K, Bd, variant=0, out=tmp)
+            run32(); run32()
+            ts = []
+            for _ in range(7):
+                if l2_flush is not None:
+                    l2_flush.sum()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run32(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms32 = sh.reduce_max(statistics.median(ts), device="cuda")
+            den = (Cd.abs() + tmp.abs()).clamp_min(1e-30)
+            fp32_path = {"kernel_rank0": b.CSR_KERNEL_NAMES.get(kv), "ms": ms32, "gflops": flops_total / (ms32 * 1e-3) / 1e9,
+                         "tensor_path_speedup": ms32 / ms_per_step,
+                         "max_abs_diff_vs_tensor_path_rank0": float((tmp - Cd).abs().max().item()),
+                         "note": "cuspmm_set_csr_tensor_mode(0): the selector restricted to the fp32 FMA kernels, same timing protocol"}
+            del tmp, den
+        except Exception as ex:
+            fp32_path = {"error": str(ex)[:200]}
+        finally:
+            b.set_csr_tensor_mode(prev)
+
     out = None
     if rank == 0:
         sm_clock = (clocks or {}).get("sm_mhz")
-        roof = roofline_record(pk, alg_l, ms_per_step, flops_l, nnz, N, sm_clock,
-                               lookup_traffic(args.workload, fmt, kernel_name) if world == 1 else None)
+        traffic = lookup_traffic(args.workload, fmt, kernel_name) if world == 1 else None
+        if kernel_name == "csr_tensor":
+            roof = tensor_roofline_record(pk, Ml, K, N, alg_l, ms_per_step, nnz, sm_clock, traffic)
+            roof["note"] = ("per step of rank 0 = csr_tc_prepare_B + memset of C + csr_tc_kernel (+ the fallback kernel, which exits at "
+                            "once); csr_tc_kernel is ~96 % of it (profiles/r02_ncu_launches_bench.csv).  A tiles are made dense in "
+                            "shared memory and multiplied on the tensor cores with a tf32 + bf16 three-product split (fp32-grade "
+                            "result, see parity); what bounds it is shared-memory bandwidth and the builders, see DESIGN.md section 4")
+        else:
+            roof = roofline_record(pk, alg_l, ms_per_step, flops_l, nnz, N, sm_clock, traffic)
+            roof["note"] = ("per launch of rank 0's kernel (algorithmic bytes of ITS panel / its device time; peak = one GPU). fp32 CUDA-core "
+                            "SpMM at this density is bound by SM-local operand bandwidth (one distinct B element per FMA), not HBM: "
+                            "smem_operand_bw = all B reads through LDS at 128 B/clk/SM; see DESIGN.md")
         roof["frac_of_binding_bound"] = max(roof["bounds_ms"].values()) / ms_per_step
         roof["kernel"] = kernel_name
-        roof["note"] = ("per launch of rank 0's kernel (algorithmic bytes of ITS panel / its device time; peak = one GPU). fp32 CUDA-core "
-                        "SpMM at this density is bound by SM-local operand bandwidth (one distinct B element per FMA), not HBM: "
-                        "smem_operand_bw = all B reads through LDS at 128 B/clk/SM; see DESIGN.md")
         imb = max(rank_nnz) * world / max(sum(rank_nnz), 1)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": "f32 (tensor cores: tf32 + bf16 three-product split, fp32 accumulate)" if kernel_name == "csr_tensor" else "f32",
+            "data": "synthetic",
             "config": {"workload": f"{args.workload}: ONE {M}x{K} A, density {density} (nnz {nnz_total}), B {K}x{N}, "
                                    f"{fmt.upper()} variant {args.variant} (0 = selector -> {kernel_name})",
                        "format": fmt, "M": M, "K": K, "N": N, "nnz": nnz_total,
@@ -734,6 +792,7 @@ def main():
             "e2e": e2e,
             "parity": parity,
             "cusparse": cusparse,
+            "fp32_path": fp32_path,
             "clocks": clocks,
         }
     # ---- N = 1 only: CPU baseline and the other formats / configs (rank 0 alone exists)

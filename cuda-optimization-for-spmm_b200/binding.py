@@ -39,6 +39,7 @@ def lib():
         L.cuspmm_spmm_coo_workspace.argtypes = [U32, U32, U32, C.c_int]
         L.cuspmm_spmm_csr.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P]
         L.cuspmm_csr_selected_variant.argtypes = [U32, U32, U32, U32, C.c_int]
+        L.cuspmm_set_csr_tensor_mode.argtypes = [C.c_int]
         L.cuspmm_spmm_csr_workspace.restype = SZ
         L.cuspmm_spmm_csr_workspace.argtypes = [U32, U32, U32, U32, C.c_int]
         L.cuspmm_spmm_csr_ws.argtypes = [P, P, P, U32, U32, U32, P, U32, SZ, P, SZ, C.c_int, P, SZ, P]
@@ -157,6 +158,11 @@ CSR_KERNEL_NAMES = {1: "csr_rowsplit_vec", 2: "csr_subwarp_vec", 3: "csr_staged"
 def csr_selected_variant(M, K, nnz, N, sell=False):
     """The variant the selector (variant 0) runs for this shape on the current device."""
     return int(lib().cuspmm_csr_selected_variant(M, K, nnz, N, 1 if sell else 0))
+
+
+def set_csr_tensor_mode(mode):
+    """1: the selector may choose the tensor-core kernel (variant 8); 0: fp32 FMA kernels only.  Returns the previous mode."""
+    return int(lib().cuspmm_set_csr_tensor_mode(1 if mode else 0))
 
 
 def spmm_coo(rowIdxs, colIdxs, vals, M, K, B, variant=0, out=None):

@@ -159,7 +159,7 @@ static int spmm_coo_dispatch(const uint32_t *rowIdxs, const uint32_t *colIdxs, c
     if (variant == 0) {   // the CSR selector decides whether the staged kernel pays; it needs row pointers
         const bool have_ws = ws && ws_bytes >= (size_t)(M + 1) * 4;
         const int cv = csr_select_variant(M, K, nnz, N, vok);
-        variant = (have_ws && (cv == 3 || cv == 5)) ? 2 : 1;
+        variant = (have_ws && (cv == 3 || cv == 5 || cv == 8)) ? 2 : 1;
     }
     if (variant == 2) {
         if (ws_bytes < (size_t)(M + 1) * 4 || !ws)

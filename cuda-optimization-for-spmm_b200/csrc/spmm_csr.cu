@@ -23,6 +23,8 @@
 // sliced-ELL layout (spmm_ell.cu calls spmm_sell_rows_dispatch).
 #include "common.cuh"
 
+#include <atomic>
+
 #include <stdlib.h>
 
 namespace cuspmm_b200 {
@@ -593,6 +595,7 @@ void quad_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_pe
 // variant 8: A tiles made dense in shared memory, tcgen05.mma with a three-product tf32 / bf16 split (spmm_csr_tc.cu); CSR only
 int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
                 const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
+bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N);   // is variant 8 expected to beat the fp32 kernels on this shape?
 // variant 6: nnz split that cuts rows, ordered carry fix-up (spmm_csr_split.cu); needs workspace
 size_t spmm_csr_split_workspace(uint32_t nnz, uint32_t N);
 int spmm_csr_split(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
@@ -618,8 +621,22 @@ static uint32_t pick_warps(uint32_t M) {
 //     ... and >= 5.5 non-zeros per staged B row and CTA  -> dual-path staged (5): part of every B chunk in tensor memory
 //   - N <= 512, or short rows (< 96 nnz/row)          -> sub-warp per row (2): 64-column tiles, many rows in flight
 //   - otherwise (wide N, long rows)                   -> warp per row, nnz-balanced (1): A is re-read N/512 times only
+// Tensor-core mode (cuspmm_set_csr_tensor_mode): 1 = the selector may choose variant 8, 0 = fp32 FMA kernels only.
+// Unset: the environment variable CUSPMM_TENSOR (0 disables) decides, default on.
+static std::atomic<int> g_tensorMode{-1};
+static bool tensor_mode_on() {
+    int m = g_tensorMode.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = getenv("CUSPMM_TENSOR");
+        m = (e && atoi(e) == 0) ? 0 : 1;
+        g_tensorMode.store(m, std::memory_order_relaxed);
+    }
+    return m != 0;
+}
+
 int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok, bool sell) {
     if (!vec_ok) return 4;
+    if (!sell && M && K && tensor_mode_on() && tc_kernel_wins(M, K, nnz, N)) return 8;
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
     // N = 128: one 128-column tile, 31 rows per CTA (N = 256 / 384 would need row-wise TMA copies of 512 bytes: 25605^2,
@@ -748,7 +765,8 @@ int spmm_csr_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const fl
 // (GL7d25, 2798 rows of 2..422 non-zeros, N = 512: 0.072 ms; cut into equal nnz ranges: see profiles/r01_real_matrices.jsonl).
 static bool prefer_split(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vok) {
     if (!vok || M == 0) return false;
-    if (csr_select_variant(M, K, nnz, N, vok, false) == 3 || csr_select_variant(M, K, nnz, N, vok, false) == 5) return false;
+    const int sel = csr_select_variant(M, K, nnz, N, vok, false);
+    if (sel == 3 || sel == 5 || sel == 8) return false;
     const uint64_t rowWarps = (uint64_t)M * ((N + 511) / 512);
     return rowWarps < (uint64_t)sm_count() * 32 && (double)nnz / M >= 16.0;
 }
@@ -782,6 +800,12 @@ int spmm_sell_rows_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, 
 }
 
 } // namespace cuspmm_b200
+
+extern "C" int cuspmm_set_csr_tensor_mode(int mode) {
+    const bool was = cuspmm_b200::tensor_mode_on();
+    cuspmm_b200::g_tensorMode.store(mode != 0 ? 1 : 0, std::memory_order_relaxed);
+    return was ? 1 : 0;
+}
 
 // what variant 0 resolves to for this shape on the current device (16-byte aligned operands assumed)
 extern "C" int cuspmm_csr_selected_variant(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int sliced_ell) {

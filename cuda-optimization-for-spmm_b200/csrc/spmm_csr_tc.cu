@@ -62,19 +62,56 @@ namespace cuspmm_b200 {
 namespace csrtc {
 
 using namespace tmemk;
+// The waits of this kernel are short and sit on the critical path of a 4-deep pipeline of ~1100-clock chunks: plain try_wait
+// polling.  (With the 2000 ns suspend-time hint the other staged kernels use, a waiter that misses the phase change sleeps the
+// hint out: the bare barrier skeleton of this kernel -- no MMA, no TMA, no building -- took 890 clocks per chunk.)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 32)         /* experiment: spin on test_wait instead of the suspending try_wait */
+    uint32_t polls = 0;
+    uint64_t t0 = 0;
+    while (!mbar_test(bar, parity)) {
+        if ((++polls & 65535u) == 0) {
+            const uint64_t now = pipe::global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > pipe::kWaitLimitNs) __trap();
+        }
+    }
+#else
+    pipe::mbar_wait<0>(bar, parity);
+#endif
+}
 
-constexpr int kTileM = 256, kTileN = 256, kKC = 16;
-constexpr int kStages = 3;
+constexpr int kTileN = 256, kKC = 16;
+constexpr int kRowsPerCta = 256;                                     // rows of A one CTA builds: two UMMA M blocks of 128
 constexpr int kBuilders = 256, kEpilogue = 128;
 constexpr int kThreads = 64 + kBuilders + kEpilogue;
-constexpr uint32_t kABytes = 32768, kBBytes = 32768;                 // per stage
-constexpr uint32_t kOffT = 0, kOffP = 16384;                         // tf32 | bf16 pairs inside a stage of A or B
+constexpr uint32_t kABytes = 32768, kBBytes = 32768;                 // per stage of A (one CTA) / per chunk record of B (256 columns)
+constexpr uint32_t kOffT = 0, kOffP = 16384;                         // tf32 | bf16 pairs inside a stage of A
 constexpr uint32_t kPrefetchChunks = 12;                             // L2 prefetch distance of the B producer, in chunks
 constexpr uint32_t kFlushChunks = 64;                                // 256 accumulation steps between two drains of the accumulators
-constexpr uint32_t kRingOff = kStages * (kABytes + kBBytes);         // [colIdxs | vals][slot 4][row 256][16 B]
-constexpr uint32_t kRingBytes = 2 * 4 * kBuilders * 16;
-constexpr uint32_t kSmemTotal = kRingOff + kRingBytes + (3 * kStages + 2) * 8 + 16 + 128;
-static_assert(kSmemTotal <= 232448, "more than 227 KB of shared memory");
+// NCTA = 1: one CTA per tile of 256 rows x 256 columns.  NCTA = 2: a CTA PAIR (cluster of two, tcgen05 cta_group::2, UMMA M = 256)
+// per tile of 512 rows x 256 columns: each CTA builds its own 256 rows of A but holds only HALF of every B chunk (128 of the
+// 256 columns), so the MMAs read B from shared memory once per 256 rows instead of once per 128, TMA writes half as much, L2
+// delivers half as much, and the space buys rings of 4 + 4 stages instead of 3 + 3.
+template <int NCTA>
+struct Cfg {
+    // the builders need more than one chunk time (clear, scatter, proxy fence, arrive): with 3 stages the issuer found the
+    // next chunk's A late by ~150 clocks every chunk.  A pair has the room for 4 (its B stages are half as large).
+    static constexpr int kStages = NCTA == 1 ? 3 : 4;
+    static constexpr int kAStages = kStages, kBStages = kStages;
+    static constexpr uint32_t kBStage = kBBytes / NCTA;               // bytes of a B chunk one CTA holds: [b_t | pairs]
+    static constexpr uint32_t kBOffP = kBStage / 2;
+    static constexpr uint32_t kBLbo = (kTileN / NCTA) * 16;           // next k group of the B operand
+    static constexpr uint32_t kAOff = 0;
+    static constexpr uint32_t kBOff = kAStages * kABytes;
+    static constexpr uint32_t kRingOff = kBOff + kBStages * kBStage;  // [colIdxs | vals][slot 4][row 256][16 B]
+    static constexpr uint32_t kRingBytes = 2 * 4 * kBuilders * 16;
+    static constexpr uint32_t kBarOff = kRingOff + kRingBytes;
+    static constexpr uint32_t kNumBars = 2 * kStages + 2;           // full, empty, accum_full, accum_empty
+    static constexpr uint32_t kSmemTotal = kBarOff + kNumBars * 8 + 16 + 128;
+    static constexpr int kTileM = kRowsPerCta * NCTA;
+    static_assert(kSmemTotal <= 232448, "more than 227 KB of shared memory");
+};
 
 struct Plan {
     uint32_t tilesN, chunks, grid, fullWaves, remTiles;
@@ -123,14 +160,22 @@ __device__ __forceinline__ uint16_t bf16_bits(float v) {
     const __nv_bfloat16 h = fabsf(v) < 1.7e38f ? __float2bfloat16_rn(v) : __float2bfloat16_rz(v);
     return __bfloat16_as_ushort(h);
 }
+// (Tried: two bf16 pieces per operand and all four cross products in one bf16 operand -- one 8-byte store per entry, one kind
+//  of MMA.  bf16 keeps 8 significant bits, two pieces 16: the dropped terms are 2^-15 |a||b|, 1.1e-5 observed on short rows.
+//  Three pieces need six products.  The tf32 main product is what makes three products enough.)
 
 // ---------------------------------------------------------------------------------------------- B -> tiled operand records
-// grid (2 * chunks, tilesN), 256 threads: thread = one column n, 8 consecutive k
+// grid (2 * chunks, tilesN), 256 threads: thread = one column n, 8 consecutive k.  A record is NCTA parts of 256 / NCTA columns,
+// each [b_t: 4 k-groups x columns x 16 B | pairs: the same shape]
+template <int NCTA>
 __global__ void __launch_bounds__(256)
 csr_tc_prepare_B(const float *__restrict__ B, uint32_t K, uint32_t N, size_t ldb, unsigned char *__restrict__ Bt, uint32_t chunks,
                  uint32_t *__restrict__ flag) {
+    using CF = Cfg<NCTA>;
+    constexpr uint32_t kCols = kTileN / NCTA;
     const uint32_t half = blockIdx.x & 1u, chunk = blockIdx.x >> 1, ct = blockIdx.y;
-    const uint32_t nloc = threadIdx.x, n = ct * kTileN + nloc;
+    const uint32_t n = ct * kTileN + threadIdx.x;
+    const uint32_t part = threadIdx.x / kCols, nloc = threadIdx.x % kCols;
     const uint32_t k0 = blockIdx.x * 8u;
     float b[8];
 #pragma unroll
@@ -144,10 +189,10 @@ csr_tc_prepare_B(const float *__restrict__ B, uint32_t K, uint32_t N, size_t ldb
         bad |= !(fabsf(b[j]) < 1.7e38f);
     }
     if (__any_sync(0xFFFFFFFFu, bad) && lane_id() == 0) atomicOr(flag, 1u);
-    unsigned char *rec = Bt + ((size_t)ct * chunks + chunk) * kBBytes;
-    float4 *pt = reinterpret_cast<float4 *>(rec + kOffT + (half * 2u) * 4096u + nloc * 16u);
+    unsigned char *rec = Bt + ((size_t)ct * chunks + chunk) * kBBytes + part * CF::kBStage;
+    float4 *pt = reinterpret_cast<float4 *>(rec + (half * 2u) * CF::kBLbo + nloc * 16u);
     pt[0] = make_float4(t[0], t[1], t[2], t[3]);
-    pt[256] = make_float4(t[4], t[5], t[6], t[7]);               // next k group: 256 columns x 16 B further
+    pt[kCols] = make_float4(t[4], t[5], t[6], t[7]);             // next k group
     // the two correction products share ONE bf16 operand: per k the pair (bf16(r_b), bf16(b)) here against (bf16(a), bf16(r_a)) on
     // the A side, so that a K = 16 MMA sums  bf16(a) bf16(r_b) + bf16(r_a) bf16(b)  over 8 k
     uint4 p0, p1;
@@ -159,9 +204,9 @@ csr_tc_prepare_B(const float *__restrict__ B, uint32_t K, uint32_t N, size_t ldb
     p1.y = bf16_bits(r[5]) | ((uint32_t)bf16_bits(b[5]) << 16);
     p1.z = bf16_bits(r[6]) | ((uint32_t)bf16_bits(b[6]) << 16);
     p1.w = bf16_bits(r[7]) | ((uint32_t)bf16_bits(b[7]) << 16);
-    uint4 *pp = reinterpret_cast<uint4 *>(rec + kOffP + (half * 2u) * 4096u + nloc * 16u);
+    uint4 *pp = reinterpret_cast<uint4 *>(rec + CF::kBOffP + (half * 2u) * CF::kBLbo + nloc * 16u);
     pp[0] = p0;
-    pp[256] = p1;
+    pp[kCols] = p1;
 }
 
 // ---------------------------------------------------------------------------------------------- MMA
@@ -170,19 +215,79 @@ csr_tc_prepare_B(const float *__restrict__ B, uint32_t K, uint32_t N, size_t ldb
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+template <int NCTA>
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    if constexpr (NCTA == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+template <int NCTA>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {   // always accumulates
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u) : "memory");
+    if constexpr (NCTA == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1u) : "memory");
+}
+// arrives on bar (pair: on the barrier at this offset in BOTH CTAs) once every MMA issued so far by this thread has completed
+template <int NCTA>
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    if constexpr (NCTA == 1) tc_commit(bar);
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ bool mbar_test_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+// The per-chunk "my half is ready" of rank 1.  Relaxed: a release at cluster scope is a full memory barrier for the thread
+// (ncu: ~70x the samples of an MMA issue on that one instruction, more than a chunk time), and there is nothing of this thread's
+// to release -- what the tensor core of THIS CTA will read was written by the builders (each fenced its stores for the async
+// proxy and arrived with release on the local barrier this thread has just acquired) and by TMA (complete_tx observed).
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t *bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// wait for a phase that a thread of the OTHER CTA of the pair completes: acquire at cluster scope
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0, polls = 0;
+    uint64_t t0 = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if ((++polls & 4095u) == 0) {
+            const uint64_t now = pipe::global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > pipe::kWaitLimitNs) __trap();
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t pick(const uint4 &v, uint32_t i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
@@ -201,9 +306,6 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
     return v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
-    asm volatile("{\n\t.reg .b16 h;\n\tcvt.u16.u32 h, %1;\n\tst.shared.u16 [%0], h;\n\t}" ::"r"(addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ void sts_zero16(uint32_t addr) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
@@ -212,68 +314,89 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 }
 
 // VEC: colIdxs and vals are 16-byte aligned (blocks of 4 entries are fetched with one cp.async each)
-template <bool VEC>
+// NCTA = 2: launched in clusters of two CTAs; blockIdx.x / 2 is the pair, %cluster_ctarank the half.  Only rank 0 issues MMAs.
+//   barriers (same offsets in both CTAs): see full / empty below; accum_full is arrived in BOTH CTAs by the multicast
+//   tcgen05.commit of rank 0; accum_empty lives in rank 0 and collects the epilogue warps of both CTAs.
+template <bool VEC, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
               uint32_t M, uint32_t nnzTotal, const unsigned char *__restrict__ Bt, uint32_t N, float *__restrict__ C, size_t ldc,
               Plan pl, const uint32_t *__restrict__ flag, int vecC) {
+    using CF = Cfg<NCTA>;
+    constexpr int kStages = CF::kStages, kAStages = kStages;
     extern __shared__ __align__(128) unsigned char smem[];
     if (*flag) return;                                        // B holds a non-finite value: the fp32 kernel that follows computes C
-    unsigned char *stA = smem;
-    unsigned char *stB = smem + kStages * kABytes;
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + kRingOff + kRingBytes);
-    uint64_t *b_full = a_full + kStages;
-    uint64_t *empty = b_full + kStages;
+    unsigned char *stA = smem + CF::kAOff;
+    unsigned char *stB = smem + CF::kBOff;
+    // ONE full / empty barrier per stage (mbarrier operations cost the issuing thread ~80 clocks each, and the MMA issuer is a
+    // single thread: with separate barriers for A, B and the peer it spent more time on barriers than the MMAs of a chunk take):
+    //   full[s]   <- the 8 builder warps of this CTA + the TMA producer (its arrive.expect_tx; the bytes complete it)
+    //                + in rank 0 of a pair one arrive from rank 1, whose warp 1 waits for rank 1's own full[s]
+    //   empty[s]  <- one tcgen05.commit of the issuer (multicast into both CTAs of a pair): builders AND producer wait on it
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + CF::kBarOff);
+    uint64_t *empty = full + kStages;
     uint64_t *accum_full = empty + kStages;
     uint64_t *accum_empty = accum_full + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_empty + 1);
 
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t rank = NCTA == 1 ? 0u : cluster_ctarank();
+    const bool rank0 = rank == 0;
+    const uint32_t unit = NCTA == 1 ? blockIdx.x : blockIdx.x >> 1;      // CTA or pair: what the plan hands tiles to
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(a_full + s, kBuilders / 32); mbar_init(b_full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full + s, kBuilders / 32 + 1 + ((NCTA == 2 && rank0) ? 1 : 0));
+            mbar_init(empty + s, 1);
+        }
         mbar_init(accum_full, 1);
-        mbar_init(accum_empty, kEpilogue / 32);
+        mbar_init(accum_empty, NCTA * kEpilogue / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (NCTA == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();             // the barriers and the allocation of the other CTA exist
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    SegIter seg(pl, blockIdx.x);
+    SegIter seg(pl, unit);
     uint32_t tile, kb, ke;
     const uint32_t F = pl.flushChunks;
 
     if (warp == 0) {
-        // ---------------------------------------------------------------------------- B producer
+        // ---------------------------------------------------------------------------- B producer (this CTA's part of every chunk)
         if (lane == 0) {
             uint32_t s = 0, round = 0;                        // ring slot, times the ring has wrapped
             while (seg.next(tile, kb, ke)) {
                 const uint32_t ct = tile % pl.tilesN;
-                const unsigned char *src = Bt + ((size_t)ct * pl.chunks + kb) * kBBytes;
+                const unsigned char *src = Bt + ((size_t)ct * pl.chunks + kb) * kBBytes + rank * CF::kBStage;
                 for (uint32_t k = kb; k < ke; ++k, src += kBBytes) {
-                    // the records of the next chunks are pulled into L2 well ahead: a stage is refilled only two chunks (~2000
-                    // clocks) before it is consumed, enough for an L2 hit but not for a miss to HBM
+                    // the records of the next chunks are pulled into L2 well ahead of the copy into shared memory
                     if (k + kPrefetchChunks < pl.chunks)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)kPrefetchChunks * kBBytes), "r"(kBBytes) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)kPrefetchChunks * kBBytes), "r"(CF::kBStage) : "memory");
                     if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                    mbar_expect_tx(b_full + s, kBBytes);
-                    bulk_g2s(stB + s * kBBytes, src, kBBytes, b_full + s);
+                    mbar_expect_tx(full + s, CF::kBStage);
+                    bulk_g2s(stB + s * CF::kBStage, src, CF::kBStage, full + s);
                     if (++s == kStages) { s = 0; ++round; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idT = make_idesc(2, 128, kTileN), idH = make_idesc(1, 128, kTileN);
-            uint32_t s = 0, round = 0, pieces = 0;
+        if (lane == 0 && rank == 0) {
+            // ------------------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idT = make_idesc(2, 128 * NCTA, kTileN), idH = make_idesc(1, 128 * NCTA, kTileN);
+            uint32_t sa = 0, roundA = 0, pieces = 0;
+            bool ready = false;                               // the operands of the chunk about to be issued were seen complete already
 #ifdef CUSPMM_TC_DEBUG
-            long long dbgA = 0, dbgB = 0, dbgE = 0, dbgN = 0;
+            long long dbgA = 0, dbgE = 0, dbgN = 0, dbgR = 0;
             const long long dbgT0 = clock64();
 #endif
             while (seg.next(tile, kb, ke)) {
@@ -282,58 +405,75 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
 #ifdef CUSPMM_TC_DEBUG
                     const long long te = clock64();
 #endif
-                    if (first && pieces > 0) { mbar_wait(accum_empty, (pieces - 1) & 1); tc_fence_after(); }
-#ifdef CUSPMM_TC_DEBUG
-                    dbgE += clock64() - te;
-#endif
+                    if (first && pieces > 0) {
+                        if constexpr (NCTA == 1) mbar_wait(accum_empty, (pieces - 1) & 1); else mbar_wait_cluster(accum_empty, (pieces - 1) & 1);
+                        tc_fence_after();
+                    }
 #ifdef CUSPMM_TC_DEBUG
                     const long long t0 = clock64();
-                    mbar_wait(a_full + s, round & 1);
-                    const long long t1 = clock64();
-                    mbar_wait(b_full + s, round & 1);
-                    const long long t2 = clock64();
-                    dbgA += t1 - t0; dbgB += t2 - t1; ++dbgN;
-#else
-                    mbar_wait(a_full + s, round & 1);
-                    mbar_wait(b_full + s, round & 1);
+#endif
+                    if (!ready) {
+                        if constexpr (NCTA == 1) mbar_wait(full + sa, roundA & 1); else mbar_wait_cluster(full + sa, roundA & 1);
+                    }
+#ifdef CUSPMM_TC_DEBUG
+                    dbgE += t0 - te; dbgA += clock64() - t0; ++dbgN; dbgR += ready;
 #endif
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(stA + s * kABytes), b0 = smem_u32(stB + s * kBBytes);
-                    // B operand (N = 256 columns of the tile): next k group 4096 B, next 8 columns 128 B.  k groups 0..3 of a tile
-                    // hold 4 k each: a tf32 MMA (K = 8) and a pair MMA (K = 16 = 8 k x 2) both take two of them
-                    const uint64_t bT0 = make_desc(b0 + kOffT, 4096, 128), bT1 = make_desc(b0 + kOffT + 8192, 4096, 128);
-                    const uint64_t bP0 = make_desc(b0 + kOffP, 4096, 128), bP1 = make_desc(b0 + kOffP + 8192, 4096, 128);
+                    const uint32_t a0 = smem_u32(stA + sa * kABytes), b0 = smem_u32(stB + sa * CF::kBStage);
+                    // B operand (N = 256 columns; a pair holds 128 of them per CTA): k groups 0..3 of a tile hold 4 k each: a tf32
+                    // MMA (K = 8) and a pair MMA (K = 16 = 8 k x 2) both take two of them; next 8 columns 128 B
+                    const uint64_t bT0 = make_desc(b0, CF::kBLbo, 128), bT1 = make_desc(b0 + 2 * CF::kBLbo, CF::kBLbo, 128);
+                    const uint64_t bP0 = make_desc(b0 + CF::kBOffP, CF::kBLbo, 128), bP1 = make_desc(b0 + CF::kBOffP + 2 * CF::kBLbo, CF::kBLbo, 128);
 #pragma unroll
                     for (uint32_t m = 0; m < 2; ++m) {
-                        // A operand (M = 128 rows): next k group 2048 B, next 8 rows 128 B
+                        // A operand (M = 128 rows per CTA): next k group 2048 B, next 8 rows 128 B
                         const uint32_t d = tmem_base + m * kTileN;
                         const uint32_t am = a0 + m * 8192;
-                        umma_tf32(d, make_desc(am + kOffT, 2048, 128), bT0, idT, first ? 0u : 1u);
-                        umma_tf32(d, make_desc(am + kOffT + 4096, 2048, 128), bT1, idT, 1u);
-                        umma_bf16(d, make_desc(am + kOffP, 2048, 128), bP0, idH);         // bf16(a) x bf16(r_b) + bf16(r_a) x bf16(b), k 0..7
-                        umma_bf16(d, make_desc(am + kOffP + 4096, 2048, 128), bP1, idH);  // k 8..15
+#if defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 4)
+                        if (pl.chunks == 0xFFFFFFFFu)
+#endif
+                        {
+                        umma_tf32<NCTA>(d, make_desc(am + kOffT, 2048, 128), bT0, idT, first ? 0u : 1u);
+                        umma_tf32<NCTA>(d, make_desc(am + kOffT + 4096, 2048, 128), bT1, idT, 1u);
+                        umma_bf16<NCTA>(d, make_desc(am + kOffP, 2048, 128), bP0, idH);         // bf16(a) x bf16(r_b) + bf16(r_a) x bf16(b), k 0..7
+                        umma_bf16<NCTA>(d, make_desc(am + kOffP + 4096, 2048, 128), bP1, idH);  // k 8..15
+                        }
                     }
-                    tc_commit(empty + s);                     // the stage may be rebuilt once these MMAs have read it
-                    if (++s == kStages) { s = 0; ++round; }
-                    if ((k + 1 - kb) % F == 0 || k + 1 == ke) { tc_commit(accum_full); ++pieces; }
+                    umma_commit<NCTA>(empty + sa);            // the stage may be refilled once these MMAs have read it
+                    if (++sa == kStages) { sa = 0; ++roundA; }
+                    if ((k + 1 - kb) % F == 0 || k + 1 == ke) { umma_commit<NCTA>(accum_full); ++pieces; }
+                    // The tensor pipe is still busy with what was just queued: look at the barrier of the NEXT chunk now (one
+                    // non-blocking test), so that its latency is not paid after the queue has run dry.
+                    if constexpr (NCTA == 1) ready = mbar_test(full + sa, roundA & 1); else ready = mbar_test_cluster(full + sa, roundA & 1);
                 }
             }
 #ifdef CUSPMM_TC_DEBUG
-            if (blockIdx.x == 0 || blockIdx.x == 77)
-                printf("cta %u: chunks %lld, total %lld clk (%lld per chunk); issuer waited: A %lld, B %lld, drain %lld per chunk\n", blockIdx.x, dbgN,
-                       clock64() - dbgT0, (clock64() - dbgT0) / dbgN, dbgA / dbgN, dbgB / dbgN, dbgE / dbgN);
+            if (unit == 0 || unit == 37)
+                printf("unit %u: chunks %lld (%lld found ready early), %lld clk per chunk; issuer waited per chunk: operands %lld, drain %lld\n",
+                       unit, dbgN, dbgR, (clock64() - dbgT0) / dbgN, dbgA / dbgN, dbgE / dbgN);
 #endif
+        } else if (NCTA == 2 && lane == 0) {
+            // ------------------------------------------------------------------------ rank 1: tell rank 0 when this half is ready
+            uint32_t sa = 0, roundA = 0;
+            while (seg.next(tile, kb, ke)) {
+                for (uint32_t k = kb; k < ke; ++k) {
+                    mbar_wait(full + sa, roundA & 1);
+                    mbar_arrive_remote_relaxed(full + sa, 0);
+                    if (++sa == kStages) { sa = 0; ++roundA; }
+                }
+            }
         }
     } else if (warp < 2 + kBuilders / 32) {
         // ---------------------------------------------------------------------------- builders
-        const uint32_t t = threadIdx.x - 64;                  // row of the tile this thread builds
+        const uint32_t t = threadIdx.x - 64;                  // row this thread builds: M block t / 128, row t % 128 of this CTA's half
         const uint32_t mblk = t >> 7, rowInBlk = t & 127;
         const uint32_t offT = kOffT + mblk * 8192 + rowInBlk * 16;
-        const uint32_t ring = smem_u32(smem + kRingOff) + t * 16u;       // this row's slot 0 of the colIdxs ring; vals 16 KB further
+        const uint32_t rowInTile = NCTA == 1 ? t : mblk * 256 + rank * 128 + rowInBlk;
+        const uint32_t ring = smem_u32(smem + CF::kRingOff) + t * 16u;   // this row's slot 0 of the colIdxs ring; vals 16 KB further
         const uint32_t stA32 = smem_u32(stA);
         uint32_t s = 0, round = 0;
         while (seg.next(tile, kb, ke)) {
-            const uint32_t r = (tile / pl.tilesN) * kTileM + t;
+            const uint32_t r = (tile / pl.tilesN) * CF::kTileM + rowInTile;
             uint32_t p = 0, end = 0;
             if (r < M) {
                 p = __ldg(rowPtrs + r);
@@ -353,8 +493,7 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
             // per warp and register, so a lane shifting its FIFO waits for the load another lane issued a moment ago -- ncu on the
             // first version: 29 % of all samples on that move, one exposed memory latency per chunk.)  Refills are issued at the
             // start of a chunk, one commit group per chunk, and cp.async.wait_group 2 makes the groups older than two chunks
-            // visible (waiting for the group of the previous chunk exposed the memory latency of every chunk: 2.1 ms at 2 % density
-            // where the tensor pipe needs 1.3): a block is requested 12..16 entries before it is read.  Entry p of the row lives at
+            // visible: a block is requested 12..16 entries before it is read.  Entry p of the row lives at
             // ring + (p / 4 % 4) * 4096 + (p % 4) * 4.
             uint32_t fb = p & ~3u;                            // next block to request
             uint32_t lb = fb;                                 // entries below lb have landed
@@ -379,30 +518,49 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                 }
             };
 
-            uint32_t fbPrev = fb;                             // fb before the refill of the previous chunk
-            for (uint32_t k = kb; k < ke; ++k) {
+            // A pass builds kPass consecutive chunks.  Two per pass (amortising the chain barrier wake-up -> clears -> LDS -> stores
+            // -> proxy fence -> arrive over 32 columns) was measured and is slower from 10 % density (2.61 vs 2.52 ms, 7.5 vs 6.4 ms
+            // at 50 %): the scatter loop of a pass is as long as its longest row, and the issuer waits for the whole pass.
+            constexpr uint32_t kPass = 1u;
+            uint32_t fbPrev = fb;                             // fb before the refill of the previous pass
+            for (uint32_t k = kb; k < ke;) {
+                const uint32_t nc = (kPass == 2 && k + 1 < ke) ? 2u : 1u;       // chunks of this pass
                 const uint32_t fbBefore = fb;
+#if !(defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 2))
                 refill();
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (k == kb) { asm volatile("cp.async.wait_group 0;" ::: "memory"); lb = fb; }
-                else {                                        // all groups but the last two have landed: requested >= 2 chunks ago
+                else {                                        // all groups but the last two have landed: requested >= 2 passes ago
                     asm volatile("cp.async.wait_group 2;" ::: "memory");
                     if (fbPrev > lb) lb = fbPrev;
                 }
+#endif
                 fbPrev = fbBefore;
+                uint32_t s1 = s + 1, round1 = round;
+                if (s1 == kAStages) { s1 = 0; ++round1; }
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                const uint32_t a = stA32 + s * kABytes;
-                const uint32_t aT = a + offT;
+                if (nc == 2 && round1 > 0) mbar_wait(empty + s1, (round1 - 1) & 1);
+                const uint32_t aT = stA32 + s * kABytes + offT;
+                const uint32_t aT1 = stA32 + s1 * kABytes + offT;
+#if !(defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 2))
 #pragma unroll
                 for (int g = 0; g < 4; ++g) { sts_zero16(aT + g * 2048); sts_zero16(aT + kOffP + g * 2048); }
-                const uint32_t k0 = k * kKC;
+                if (nc == 2) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) { sts_zero16(aT1 + g * 2048); sts_zero16(aT1 + kOffP + g * 2048); }
+                }
+#endif
+                const uint32_t k0 = k * kKC, span = nc * kKC;
                 for (;;) {
+#if defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 2)
+                    break;
+#endif
                     const uint32_t stop = end < lb ? end : lb;
                     bool done = false;
                     while (p < stop) {
                         const uint32_t ea = ring + ((p & 12u) << 10) + ((p & 3u) << 2);
                         const uint32_t kk = lds_u32(ea) - k0;                    // columns ascend and are >= k0 here
-                        if (kk >= (uint32_t)kKC) { done = true; break; }
+                        if (kk >= span) { done = true; break; }
                         const float v = __uint_as_float(lds_u32(ea + 16384u));
                         const uint32_t bits = __float_as_uint(v);
                         uint32_t tb = (bits + 0x1000u) & 0xFFFFE000u;          // tf32, round to nearest (ties away)
@@ -421,21 +579,27 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(res), "f"(v));
                         }
                         // tf32 tile and pair tile have the same geometry (4 k per 16-byte core-matrix row), 16 KB apart
-                        const uint32_t dstT = aT + ((kk & 12u) << 9) + ((kk & 3u) << 2);
+                        const uint32_t dstT = ((kk & 16u) ? aT1 : aT) + ((kk & 12u) << 9) + ((kk & 3u) << 2);
                         sts_u32(dstT, tb);
                         sts_u32(dstT + kOffP, pk);
                         ++p;
                     }
                     if (done || p >= end) break;
-                    // the row has more entries, but they are not known to have landed (a chunk that used more than ~2 blocks)
+                    // the row has more entries, but they are not known to have landed (a pass that used more than ~2 blocks)
                     if (p >= fb) { refill(); asm volatile("cp.async.commit_group;" ::: "memory"); }
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     lb = fb;
                 }
+#if !(defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 8))
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core (async proxy) reads
+#endif
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a_full + s);
-                if (++s == kStages) { s = 0; ++round; }
+                if (lane == 0) {
+                    mbar_arrive(full + s);
+                    if (nc == 2) mbar_arrive(full + s1);
+                }
+                k += nc;
+                s += nc; if (s >= kAStages) { s -= kAStages; ++round; }
             }
         }
     } else {
@@ -455,7 +619,7 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                 tc_fence_after();
 #pragma unroll 1
                 for (uint32_t em = 0; em < 2; ++em) {
-                    const uint32_t er = rt * kTileM + em * 128 + q * 32 + lane;
+                    const uint32_t er = rt * CF::kTileM + (NCTA == 1 ? em * 128 : em * 256 + rank * 128) + q * 32 + lane;
                     float *crow = C + (size_t)er * ldc + (size_t)ct * kTileN;
 #pragma unroll 1
                     for (uint32_t cb = 0; cb < kTileN / 32; ++cb) {
@@ -496,16 +660,20 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(accum_empty);
+                if (lane == 0) {
+                    if (NCTA == 1 || rank == 0) mbar_arrive(accum_empty); else mbar_arrive_remote(accum_empty, 0);
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (NCTA == 2) cluster_sync_all();             // nobody frees tensor memory (or leaves) while the other CTA may still use it
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if constexpr (NCTA == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -557,32 +725,39 @@ static cudaMemPool_t tc_pool(int dev) {
     return pools[dev];
 }
 
+// Does the tensor-core kernel (work ~ Mpad x K x Npad, independent of nnz) beat the fp32 kernels (work ~ nnz x N)?
+// r = nnz x N / (Mpad x K x Npad) is the useful fraction of the dense work.  Measured cross-over (profiles/r02_tc_sweep.jsonl,
+// 117 shapes: squares 4096..25605, N 128..2048, 2..50 % dense, row panels of the BASELINE matrix, FFN shapes): r ~ 0.05 at
+// N = 512, ~0.04 for N <= 256 (where the fp32 staged kernel does not apply) and for N >= 1024; small problems pay the fixed cost
+// of the three launches and the partly filled last wave: x (1 + 3.7e9 / dense work).  Above the cross-over the gain grows
+// quickly: 1.4-2.7x at 10 %, 2-5.6x from 20 %.
+bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N) {
+    if (M == 0 || K == 0 || N == 0) return false;
+    const double Mpad = (double)((M + 511u) / 512u) * 512.0, Npad = (double)((N + 255u) / 256u) * 256.0;
+    const double dense = Mpad * (double)K * Npad;
+    const double r = (double)nnz * (double)N / dense;
+    const double base = N <= 256 ? 0.040 : (N <= 512 ? 0.052 : 0.042);
+    return r >= base * (1.0 + 3.7e9 / dense);
+}
+
 size_t csr_tc_workspace_bytes(uint32_t K, uint32_t N) {
     const uint64_t tilesN = (N + csrtc::kTileN - 1) / csrtc::kTileN, chunks = (K + csrtc::kKC - 1) / csrtc::kKC;
     return (size_t)(tilesN * chunks * csrtc::kBBytes + 256);
 }
 
-// variant 8 of the CSR kernels.  Rows must be sorted by column (as for variants 3, 5, 7).
-int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
-                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+template <int NCTA>
+static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
+                  const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaMemPool_t pool, cudaStream_t st) {
     using namespace csrtc;
-    if (K == 0) {
-        CUSPMM_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
-        return CUSPMM_OK;
-    }
-    int dev = 0;
-    CUSPMM_CUDA(cudaGetDevice(&dev));
-    cudaMemPool_t pool = tc_pool(dev);
-    if (!pool) return set_error(CUSPMM_ERR_CUDA, "no memory pool for the tiled copy of B on device %d", dev);
-
+    using CF = Cfg<NCTA>;
     Plan pl;
     pl.tilesN = (N + kTileN - 1) / kTileN;
     pl.chunks = (K + kKC - 1) / kKC;
-    const uint32_t tilesM = (M + kTileM - 1) / kTileM;
+    const uint32_t tilesM = (M + CF::kTileM - 1) / CF::kTileM;
     const uint64_t tiles = (uint64_t)tilesM * pl.tilesN;
     const uint64_t units = tiles * pl.chunks;
-    // one CTA per SM; with little work, at least 8 chunks per CTA
-    uint64_t grid = (uint64_t)sm_count();
+    // one CTA (or pair) per SM (or two); with little work, at least 8 chunks each
+    uint64_t grid = (uint64_t)sm_count() / NCTA;
     if (units / 8 < grid) grid = units / 8 ? units / 8 : 1;
     pl.grid = (uint32_t)grid;
     pl.fullWaves = (uint32_t)(tiles / grid);
@@ -598,7 +773,7 @@ int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
     int rc = CUSPMM_OK;
     do {
         if (cudaMemsetAsync(flag, 0, sizeof(uint32_t), st) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "memset of the flag failed"); break; }
-        csr_tc_prepare_B<<<dim3(2 * pl.chunks, pl.tilesN), 256, 0, st>>>(B, K, N, ldb, ws, pl.chunks, flag);
+        csr_tc_prepare_B<NCTA><<<dim3(2 * pl.chunks, pl.tilesN), 256, 0, st>>>(B, K, N, ldb, ws, pl.chunks, flag);
         if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_prepare_B failed"); break; }
         count_launch();
         // every tile is drained into C piece by piece with red.add (only a tile that is a single piece is stored): C starts at zero
@@ -609,10 +784,26 @@ int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
         }
         const bool vecA = ((reinterpret_cast<uintptr_t>(colIdxs) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
         const int vecC = (N % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-        auto kern = vecA ? csr_tc_kernel<true> : csr_tc_kernel<false>;
-        if (set_smem_once(kern, kSmemTotal) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "cannot reserve %u bytes of shared memory", kSmemTotal); break; }
-        kern<<<pl.grid, kThreads, kSmemTotal, st>>>(rowPtrs, colIdxs, vals, M, nnz, ws, N, C, ldc, pl, flag, vecC);
-        if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_kernel failed: %s", cudaGetErrorString(cudaPeekAtLastError())); break; }
+        auto kern = vecA ? csr_tc_kernel<true, NCTA> : csr_tc_kernel<false, NCTA>;
+        if (set_smem_once(kern, CF::kSmemTotal) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "cannot reserve %u bytes of shared memory", CF::kSmemTotal); break; }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(pl.grid * NCTA, 1, 1);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.dynamicSmemBytes = CF::kSmemTotal;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = NCTA;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const unsigned char *wsc = ws;
+        const uint32_t *flagc = flag;
+        if (cudaLaunchKernelEx(&cfg, kern, rowPtrs, colIdxs, vals, M, nnz, wsc, N, C, ldc, pl, flagc, vecC) != cudaSuccess) {
+            rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_kernel failed: %s", cudaGetErrorString(cudaPeekAtLastError()));
+            break;
+        }
         count_launch();
         csr_tc_fallback_kernel<<<(unsigned)sm_count() * 4, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc, flag);
         if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_fallback_kernel failed"); break; }
@@ -620,6 +811,23 @@ int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
     } while (0);
     cudaFreeAsync(ws, st);
     return rc;
+}
+
+// variant 8 of the CSR kernels.  Rows must be sorted by column (as for variants 3, 5, 7).
+int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
+                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+    if (K == 0) {
+        CUSPMM_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+        return CUSPMM_OK;
+    }
+    int dev = 0;
+    CUSPMM_CUDA(cudaGetDevice(&dev));
+    cudaMemPool_t pool = tc_pool(dev);
+    if (!pool) return set_error(CUSPMM_ERR_CUDA, "no memory pool for the tiled copy of B on device %d", dev);
+    // tuning hook: CUSPMM_TC_PAIR=0 runs one CTA per 256-row tile (cta_group::1) instead of CTA pairs on 512-row tiles
+    static const int pairEnv = getenv("CUSPMM_TC_PAIR") ? atoi(getenv("CUSPMM_TC_PAIR")) : 1;
+    if (pairEnv) return run_tc<2>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
+    return run_tc<1>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
 }
 
 } // namespace cuspmm_b200

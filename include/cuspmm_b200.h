@@ -91,6 +91,12 @@ int cuspmm_spmm_csr(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs_dev, co
                     uint32_t M, uint32_t K, uint32_t nnz,
                     const float *B_dev, uint32_t N, size_t ldb,
                     float *C_dev, size_t ldc, int variant, void *stream);
+/* Tensor-core mode of the CSR selector (and of everything built on it: COO variant 0 / 2, the host-buffer and multi-GPU CSR
+ * entries).  1 (default): variant 0 may resolve to variant 8 where it is expected to be faster (from ~5 % density on large
+ * matrices; results then agree with the fp32 kernels to ~5e-7 of sum|a||b|, not bit for bit).  0: fp32 FMA kernels only, every
+ * variant 0 result bit-identical to variants 1..5.  The environment variable CUSPMM_TENSOR=0 sets the initial mode to 0.
+ * Process-wide; returns the previous mode. */
+int cuspmm_set_csr_tensor_mode(int mode);
 /* The kernel variant 0 resolves to for this shape on the current device, assuming 16-byte aligned operands (sliced_ell != 0:
  * the same question for cuspmm_spmm_sell, answered in CSR variant numbers).  bench.py records it beside every measurement. */
 int cuspmm_csr_selected_variant(uint32_t M, uint32_t K, uint32_t nnz, uint32_t N, int sliced_ell);

@@ -33,6 +33,7 @@ def b():
     from __graft_entry__ import load_package
     pkg = load_package()
     pkg.lib()
+    pkg.binding.set_csr_tensor_mode(1)
     return pkg.binding
 
 
@@ -209,3 +210,60 @@ def test_baseline_config_full_size(b, wl):
     # a second run: same result within the arrival order of the few tiles that two CTAs share
     C2 = b.spmm_csr(rp, ci, va, M, K, Bd, variant=V)
     assert ((C - C2).abs() / den.clamp_min(1e-30)).max().item() <= 1e-6
+
+
+# ------------------------------------------------------------------ the selector with the tensor kernel in it
+def test_selector_rules(b):
+    sel = b.csr_selected_variant
+    assert sel(25605, 25605, 65571195, 512) == 8                 # BASELINE: 10 % dense
+    assert sel(25605, 25605, 13111101, 512) != 8                 # 2 %: the fp32 kernels win
+    assert sel(4096, 4096, 1678023, 512) == 8 and sel(4096, 4096, 838880, 512) != 8
+    assert sel(3200, 25605, 8196778, 512) == 8                   # an 8-GPU row panel of the BASELINE matrix
+    assert sel(300, 200, 6000, 512) != 8                         # small: fixed costs
+    assert sel(25605, 25605, 65571195, 512, sell=True) != 8      # the kernel reads CSR, not sliced ELL
+    assert sel(25605, 25605, 65571195, 510) in (1, 2, 4, 8)
+    prev = b.set_csr_tensor_mode(0)
+    try:
+        assert prev == 1 and sel(25605, 25605, 65571195, 512) == 5
+    finally:
+        b.set_csr_tensor_mode(1)
+
+
+def test_variant0_paths_with_tensor_selection(b, wl):
+    """4096^2, 20 % dense, N = 512: variant 0 resolves to 8 for CSR, for COO (device COO -> CSR + selector) and inside the
+    host-buffer and multi-GPU entries; everything within the tolerance of the oracle (sampled rows) and of the fp32 kernel."""
+    import torch
+    M = K = 4096
+    N = 512
+    rp, ci, va = wl.gen_csr_device(M, K, 0.20, seed=41)
+    Bd = wl.gen_dense_device(K, N, seed=42)
+    nnz = int(ci.numel())
+    assert b.csr_selected_variant(M, K, nnz, N) == 8
+    ref = b.spmm_csr(rp, ci, va, M, K, Bd, variant=1)
+    den = b.spmm_csr(rp, ci, va.abs(), M, K, Bd.abs(), variant=1).clamp_min(1e-30)
+    Bh = Bd.cpu().numpy()
+
+    def close(C, what):
+        assert ((C - ref).abs() / den).max().item() <= 2e-6, what
+        assert not (C == ref).all().item(), what + ": bit-identical to the fp32 kernel -- the tensor kernel did not run"
+
+    c0 = b.spmm_csr(rp, ci, va, M, K, Bd, variant=0)
+    close(c0, "csr")
+    for r in (0, 255, 256, 2047, 4095):
+        srp, sci, sva = wl.csr_sample_to_host(rp, ci, va, r, r + 1)
+        a = orc.CSR(1, K, srp, sci, sva)
+        assert orc.max_rel_err(c0[r:r + 1].cpu().numpy(), orc.spmm_csr(a, Bh), orc.absprod_csr(a, Bh)) <= TOL
+    rows = torch.repeat_interleave(torch.arange(M, device="cuda", dtype=torch.int32), (rp[1:] - rp[:-1]).to(torch.int64))
+    close(b.spmm_coo(rows, ci, va, M, K, Bd, variant=0), "coo")
+    C_h = torch.empty((M, N), dtype=torch.float32).pin_memory()
+    b.spmm_csr_host(rp.cpu().pin_memory(), ci.cpu().pin_memory(), va.cpu().pin_memory(), M, K, Bd.cpu().pin_memory(), C_h)
+    close(C_h.cuda(), "csr_host")
+    n = min(2, torch.cuda.device_count())
+    plan = b.MgpuPlan(n, rp.cpu().numpy().view(np.uint32), ci.cpu().numpy().view(np.uint32), va.cpu().numpy(), M, K, N)
+    try:
+        plan.set_B(Bh)
+        plan.run(variant=0, gather=True, iters=1)
+        close(torch.from_numpy(plan.get_C()).cuda(), "mgpu")
+    finally:
+        plan.close()
+    torch.cuda.set_device(0)
