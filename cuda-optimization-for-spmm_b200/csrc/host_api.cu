@@ -740,9 +740,27 @@ extern "C" int cuspmm_mgpu_set_B(cuspmmMgpuPlan pl, const float *B, uint32_t N) 
     return CUSPMM_OK;
 }
 
+namespace cuspmm_b200 { int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok, bool sell); }   // spmm_csr.cu
+
+// Will this multiply run the tensor-core CSR kernel?  That kernel ACCUMULATES into C (memset + red.add of partial tiles every 64
+// chunks): aimed at another GPU's memory that is dozens of round trips of atomics over NVLink per element (measured: 2.5 ms on one
+// GPU, 4.9 ms on eight with the peer-store gather).  Such panels are computed into the panel's own C and sent with one peer copy.
+static bool mgpu_uses_tensor_kernel(cuspmmMgpuPlan pl, const MgpuPanel &q, int variant) {
+    if (pl->fmt != MG_CSR && pl->fmt != MG_COO) return false;
+    if (variant == 8 && pl->fmt == MG_CSR) return true;
+    if (!(variant == 0 || (variant == 2 && pl->fmt == MG_COO))) return false;
+    return cuspmm_b200::csr_select_variant(q.r1 - q.r0, pl->K, q.cnt, pl->N, pl->N % 4 == 0, false) == 8;
+}
+
 // one multiply of panel q into Cdst on its stream (the current device is q.dev)
 static int mgpu_launch(cuspmmMgpuPlan pl, MgpuPanel &q, int variant, float *Cdst) {
     const uint32_t N = pl->N, rows = q.r1 - q.r0;
+    if (Cdst != q.C && q.dev != pl->p[0].dev && mgpu_uses_tensor_kernel(pl, q, variant)) {
+        int rc = mgpu_launch(pl, q, variant, q.C);
+        if (rc) return rc;
+        CUSPMM_CUDA(cudaMemcpyPeerAsync(Cdst, pl->p[0].dev, q.C, q.dev, (size_t)rows * N * sizeof(float), q.st));
+        return CUSPMM_OK;
+    }
     switch (pl->fmt) {
     case MG_CSR:
         return spmm_csr_dispatch(q.ptrs, q.cols, q.vals, rows, pl->K, q.cnt, q.B, N, N, Cdst, N, variant, q.st);
