@@ -47,8 +47,8 @@
 // (drains of one CTA, partial tiles of several) meet in C through red.add on a zeroed C; the pieces of one CTA arrive in
 // program order, those of two CTAs that share a tile in arrival order (run-to-run differences in the last bits of those tiles).
 //
-// Warp roles (448 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = builders,
-// warps 10..13 = epilogue (tcgen05.ld 32x32b.x32 -> 16-byte reductions / stores).
+// Warp roles (480 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer of M block 0, warps 2..9 = builders,
+// warps 10..13 = epilogue (tcgen05.ld 32x32b.x32 -> 16-byte reductions / stores), warp 14 = MMA issuer of M block 1.
 //
 // Semantics that differ from the sparse kernels: a zero of A is multiplied with B, so an Inf/NaN anywhere in B would poison
 // rows that never reference it.  The prepare kernel therefore raises a device flag when B holds a non-finite value (or one
@@ -63,28 +63,14 @@ namespace csrtc {
 
 using namespace tmemk;
 // The waits of this kernel are short and sit on the critical path of a 4-deep pipeline of ~1100-clock chunks: plain try_wait
-// polling.  (With the 2000 ns suspend-time hint the other staged kernels use, a waiter that misses the phase change sleeps the
-// hint out: the bare barrier skeleton of this kernel -- no MMA, no TMA, no building -- took 890 clocks per chunk.)
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-#if defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 32)         /* experiment: spin on test_wait instead of the suspending try_wait */
-    uint32_t polls = 0;
-    uint64_t t0 = 0;
-    while (!mbar_test(bar, parity)) {
-        if ((++polls & 65535u) == 0) {
-            const uint64_t now = pipe::global_ns();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > pipe::kWaitLimitNs) __trap();
-        }
-    }
-#else
-    pipe::mbar_wait<0>(bar, parity);
-#endif
-}
+// polling (no suspend-time hint; spinning on test_wait instead made no difference).
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { pipe::mbar_wait<0>(bar, parity); }
 
 constexpr int kTileN = 256, kKC = 16;
 constexpr int kRowsPerCta = 256;                                     // rows of A one CTA builds: two UMMA M blocks of 128
 constexpr int kBuilders = 256, kEpilogue = 128;
-constexpr int kThreads = 64 + kBuilders + kEpilogue;
+constexpr int kIssuers = 2;                                           // MMA-issuing threads: one per M block (accumulator)
+constexpr int kThreads = 64 + kBuilders + kEpilogue + 32;            // the last warp hosts the second issuer
 constexpr uint32_t kABytes = 32768, kBBytes = 32768;                 // per stage of A (one CTA) / per chunk record of B (256 columns)
 constexpr uint32_t kOffT = 0, kOffP = 16384;                         // tf32 | bf16 pairs inside a stage of A
 constexpr uint32_t kPrefetchChunks = 12;                             // L2 prefetch distance of the B producer, in chunks
@@ -332,7 +318,9 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
     // single thread: with separate barriers for A, B and the peer it spent more time on barriers than the MMAs of a chunk take):
     //   full[s]   <- the 8 builder warps of this CTA + the TMA producer (its arrive.expect_tx; the bytes complete it)
     //                + in rank 0 of a pair one arrive from rank 1, whose warp 1 waits for rank 1's own full[s]
-    //   empty[s]  <- one tcgen05.commit of the issuer (multicast into both CTAs of a pair): builders AND producer wait on it
+    //   empty[s]  <- one tcgen05.commit per issuer (multicast into both CTAs of a pair): builders AND producer wait on it
+    // TWO issuing threads, one per M block (independent accumulators): what a single thread does per chunk -- barrier test or wait,
+    // fence, descriptors, 8 MMAs, commit -- took longer than the tensor pipe needs for the MMAs.
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + CF::kBarOff);
     uint64_t *empty = full + kStages;
     uint64_t *accum_full = empty + kStages;
@@ -346,9 +334,9 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full + s, kBuilders / 32 + 1 + ((NCTA == 2 && rank0) ? 1 : 0));
-            mbar_init(empty + s, 1);
+            mbar_init(empty + s, kIssuers);
         }
-        mbar_init(accum_full, 1);
+        mbar_init(accum_full, kIssuers);
         mbar_init(accum_empty, NCTA * kEpilogue / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -389,57 +377,35 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == kThreads / 32 - 1) {
+        const uint32_t m = warp == 1 ? 0u : 1u;               // the M block (accumulator) this issuer owns
         if (lane == 0 && rank == 0) {
-            // ------------------------------------------------------------------------ MMA issuer
+            // ------------------------------------------------------------------------ MMA issuer of M block m
             constexpr uint32_t idT = make_idesc(2, 128 * NCTA, kTileN), idH = make_idesc(1, 128 * NCTA, kTileN);
+            const uint32_t d = tmem_base + m * kTileN;
             uint32_t sa = 0, roundA = 0, pieces = 0;
             bool ready = false;                               // the operands of the chunk about to be issued were seen complete already
-#ifdef CUSPMM_TC_DEBUG
-            long long dbgA = 0, dbgE = 0, dbgN = 0, dbgR = 0;
-            const long long dbgT0 = clock64();
-#endif
             while (seg.next(tile, kb, ke)) {
                 for (uint32_t k = kb; k < ke; ++k) {
-                    const bool first = (k - kb) % F == 0;     // first chunk of a piece: the accumulators start over
-#ifdef CUSPMM_TC_DEBUG
-                    const long long te = clock64();
-#endif
+                    const bool first = (k - kb) % F == 0;     // first chunk of a piece: the accumulator starts over
                     if (first && pieces > 0) {
                         if constexpr (NCTA == 1) mbar_wait(accum_empty, (pieces - 1) & 1); else mbar_wait_cluster(accum_empty, (pieces - 1) & 1);
                         tc_fence_after();
                     }
-#ifdef CUSPMM_TC_DEBUG
-                    const long long t0 = clock64();
-#endif
                     if (!ready) {
                         if constexpr (NCTA == 1) mbar_wait(full + sa, roundA & 1); else mbar_wait_cluster(full + sa, roundA & 1);
                     }
-#ifdef CUSPMM_TC_DEBUG
-                    dbgE += t0 - te; dbgA += clock64() - t0; ++dbgN; dbgR += ready;
-#endif
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(stA + sa * kABytes), b0 = smem_u32(stB + sa * CF::kBStage);
-                    // B operand (N = 256 columns; a pair holds 128 of them per CTA): k groups 0..3 of a tile hold 4 k each: a tf32
-                    // MMA (K = 8) and a pair MMA (K = 16 = 8 k x 2) both take two of them; next 8 columns 128 B
-                    const uint64_t bT0 = make_desc(b0, CF::kBLbo, 128), bT1 = make_desc(b0 + 2 * CF::kBLbo, CF::kBLbo, 128);
-                    const uint64_t bP0 = make_desc(b0 + CF::kBOffP, CF::kBLbo, 128), bP1 = make_desc(b0 + CF::kBOffP + 2 * CF::kBLbo, CF::kBLbo, 128);
-#pragma unroll
-                    for (uint32_t m = 0; m < 2; ++m) {
-                        // A operand (M = 128 rows per CTA): next k group 2048 B, next 8 rows 128 B
-                        const uint32_t d = tmem_base + m * kTileN;
-                        const uint32_t am = a0 + m * 8192;
-#if defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 4)
-                        if (pl.chunks == 0xFFFFFFFFu)
-#endif
-                        {
-                        umma_tf32<NCTA>(d, make_desc(am + kOffT, 2048, 128), bT0, idT, first ? 0u : 1u);
-                        umma_tf32<NCTA>(d, make_desc(am + kOffT + 4096, 2048, 128), bT1, idT, 1u);
-                        umma_bf16<NCTA>(d, make_desc(am + kOffP, 2048, 128), bP0, idH);         // bf16(a) x bf16(r_b) + bf16(r_a) x bf16(b), k 0..7
-                        umma_bf16<NCTA>(d, make_desc(am + kOffP + 4096, 2048, 128), bP1, idH);  // k 8..15
-                        }
-                    }
-                    umma_commit<NCTA>(empty + sa);            // the stage may be refilled once these MMAs have read it
+                    const uint32_t a0 = smem_u32(stA + sa * kABytes) + m * 8192, b0 = smem_u32(stB + sa * CF::kBStage);
+                    // Operand tiles hold 4 k-groups of 4 k: a tf32 MMA (K = 8) and a pair MMA (K = 16 = 8 k x 2) both take two of
+                    // them.  A (M = 128 rows per CTA): next k group 2048 B; B (N = 256 columns, 128 per CTA of a pair): kBLbo; next 8
+                    // rows / columns 128 B
+                    umma_tf32<NCTA>(d, make_desc(a0 + kOffT, 2048, 128), make_desc(b0, CF::kBLbo, 128), idT, first ? 0u : 1u);
+                    umma_tf32<NCTA>(d, make_desc(a0 + kOffT + 4096, 2048, 128), make_desc(b0 + 2 * CF::kBLbo, CF::kBLbo, 128), idT, 1u);
+                    // bf16(a) x bf16(r_b) + bf16(r_a) x bf16(b): k 0..7, k 8..15
+                    umma_bf16<NCTA>(d, make_desc(a0 + kOffP, 2048, 128), make_desc(b0 + CF::kBOffP, CF::kBLbo, 128), idH);
+                    umma_bf16<NCTA>(d, make_desc(a0 + kOffP + 4096, 2048, 128), make_desc(b0 + CF::kBOffP + 2 * CF::kBLbo, CF::kBLbo, 128), idH);
+                    umma_commit<NCTA>(empty + sa);            // (with the other issuer's commit) the stage may be refilled
                     if (++sa == kStages) { sa = 0; ++roundA; }
                     if ((k + 1 - kb) % F == 0 || k + 1 == ke) { umma_commit<NCTA>(accum_full); ++pieces; }
                     // The tensor pipe is still busy with what was just queued: look at the barrier of the NEXT chunk now (one
@@ -447,12 +413,7 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                     if constexpr (NCTA == 1) ready = mbar_test(full + sa, roundA & 1); else ready = mbar_test_cluster(full + sa, roundA & 1);
                 }
             }
-#ifdef CUSPMM_TC_DEBUG
-            if (unit == 0 || unit == 37)
-                printf("unit %u: chunks %lld (%lld found ready early), %lld clk per chunk; issuer waited per chunk: operands %lld, drain %lld\n",
-                       unit, dbgN, dbgR, (clock64() - dbgT0) / dbgN, dbgA / dbgN, dbgE / dbgN);
-#endif
-        } else if (NCTA == 2 && lane == 0) {
+        } else if (NCTA == 2 && lane == 0 && m == 0) {
             // ------------------------------------------------------------------------ rank 1: tell rank 0 when this half is ready
             uint32_t sa = 0, roundA = 0;
             while (seg.next(tile, kb, ke)) {
@@ -518,49 +479,35 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                 }
             };
 
-            // A pass builds kPass consecutive chunks.  Two per pass (amortising the chain barrier wake-up -> clears -> LDS -> stores
-            // -> proxy fence -> arrive over 32 columns) was measured and is slower from 10 % density (2.61 vs 2.52 ms, 7.5 vs 6.4 ms
-            // at 50 %): the scatter loop of a pass is as long as its longest row, and the issuer waits for the whole pass.
-            constexpr uint32_t kPass = 1u;
-            uint32_t fbPrev = fb;                             // fb before the refill of the previous pass
-            for (uint32_t k = kb; k < ke;) {
-                const uint32_t nc = (kPass == 2 && k + 1 < ke) ? 2u : 1u;       // chunks of this pass
+            // (Two chunks per builder pass -- amortising the chain barrier wake-up -> clears -> LDS -> stores -> proxy fence -> arrive
+            //  over 32 columns -- was measured and is slower from 10 % density: 2.61 vs 2.52 ms, 7.5 vs 6.4 ms at 50 %: the scatter
+            //  loop of a pass is as long as its longest row, and the issuer waits for the whole pass.)
+            uint32_t fbPrev = fb;                             // fb before the refill of the previous chunk
+            // (Also measured and dropped: keeping the (column, value) of entry p in registers across chunks and issuing the next
+            //  entry's ring loads before the current one's stores -- 2.65 vs 2.50 ms at 10 %: the extra state costs more than the
+            //  shared-memory round trip it hides.)
+            for (uint32_t k = kb; k < ke; ++k) {
                 const uint32_t fbBefore = fb;
-#if !(defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 2))
                 refill();
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (k == kb) { asm volatile("cp.async.wait_group 0;" ::: "memory"); lb = fb; }
-                else {                                        // all groups but the last two have landed: requested >= 2 passes ago
+                else {                                        // all groups but the last two have landed: requested >= 2 chunks ago
                     asm volatile("cp.async.wait_group 2;" ::: "memory");
                     if (fbPrev > lb) lb = fbPrev;
                 }
-#endif
                 fbPrev = fbBefore;
-                uint32_t s1 = s + 1, round1 = round;
-                if (s1 == kAStages) { s1 = 0; ++round1; }
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                if (nc == 2 && round1 > 0) mbar_wait(empty + s1, (round1 - 1) & 1);
                 const uint32_t aT = stA32 + s * kABytes + offT;
-                const uint32_t aT1 = stA32 + s1 * kABytes + offT;
-#if !(defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 2))
 #pragma unroll
                 for (int g = 0; g < 4; ++g) { sts_zero16(aT + g * 2048); sts_zero16(aT + kOffP + g * 2048); }
-                if (nc == 2) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) { sts_zero16(aT1 + g * 2048); sts_zero16(aT1 + kOffP + g * 2048); }
-                }
-#endif
-                const uint32_t k0 = k * kKC, span = nc * kKC;
+                const uint32_t k0 = k * kKC;
                 for (;;) {
-#if defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 2)
-                    break;
-#endif
                     const uint32_t stop = end < lb ? end : lb;
                     bool done = false;
                     while (p < stop) {
                         const uint32_t ea = ring + ((p & 12u) << 10) + ((p & 3u) << 2);
                         const uint32_t kk = lds_u32(ea) - k0;                    // columns ascend and are >= k0 here
-                        if (kk >= span) { done = true; break; }
+                        if (kk >= (uint32_t)kKC) { done = true; break; }
                         const float v = __uint_as_float(lds_u32(ea + 16384u));
                         const uint32_t bits = __float_as_uint(v);
                         uint32_t tb = (bits + 0x1000u) & 0xFFFFE000u;          // tf32, round to nearest (ties away)
@@ -579,30 +526,24 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                             asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk) : "f"(res), "f"(v));
                         }
                         // tf32 tile and pair tile have the same geometry (4 k per 16-byte core-matrix row), 16 KB apart
-                        const uint32_t dstT = ((kk & 16u) ? aT1 : aT) + ((kk & 12u) << 9) + ((kk & 3u) << 2);
+                        const uint32_t dstT = aT + ((kk & 12u) << 9) + ((kk & 3u) << 2);
                         sts_u32(dstT, tb);
                         sts_u32(dstT + kOffP, pk);
                         ++p;
                     }
                     if (done || p >= end) break;
-                    // the row has more entries, but they are not known to have landed (a pass that used more than ~2 blocks)
+                    // the row has more entries, but they are not known to have landed (a chunk that used more than ~2 blocks)
                     if (p >= fb) { refill(); asm volatile("cp.async.commit_group;" ::: "memory"); }
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                     lb = fb;
                 }
-#if !(defined(CUSPMM_TC_EXP) && (CUSPMM_TC_EXP & 8))
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core (async proxy) reads
-#endif
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(full + s);
-                    if (nc == 2) mbar_arrive(full + s1);
-                }
-                k += nc;
-                s += nc; if (s >= kAStages) { s -= kAStages; ++round; }
+                if (lane == 0) mbar_arrive(full + s);
+                if (++s == kAStages) { s = 0; ++round; }
             }
         }
-    } else {
+    } else {     // (the issuer warps were taken by the branch above)
         // ---------------------------------------------------------------------------- epilogue (warps 10..13)
         // TMEM lanes [32 q, 32 q + 32) are the ones this warp may read; it drains both M blocks of those lanes.  Every piece is
         // added to C (zeroed by the launcher) with red.global.add.v4.f32; a tile that is one single piece is stored.

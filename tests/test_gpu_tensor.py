@@ -68,6 +68,29 @@ def test_tensor_kernel_vs_oracle(b, M, K, N, d, skew):
     check(b, a, B)
 
 
+def _random_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        M = int(rng.integers(1, 6000))
+        K = int(rng.integers(1, 6000))
+        N = int(rng.choice([3, 64, 100, 256, 300, 512, 512, 768, 1024]))
+        d = float(rng.choice([0.001, 0.02, 0.1, 0.3, 0.6, 0.9, 1.0]))
+        if M * K * d > 6e6:
+            d = 6e6 / (M * K)
+        out.append((M, K, N, d, bool(rng.integers(0, 2)), 4000 + i))
+    return out
+
+
+@pytest.mark.parametrize("M,K,N,d,skew,seed", _random_cases(16, 77))
+def test_random_shapes(b, M, K, N, d, skew, seed):
+    """Drawn shapes: partial tiles in every dimension, several column tiles, tiles cut along K between CTA pairs, several accumulator
+    drains per tile, full rows (the slow path of the entry ring), skewed row lengths."""
+    a = random_csr(M, K, d, seed=seed, skew=skew)
+    B = np.random.default_rng(seed + 1).uniform(-1, 1, (K, N)).astype(np.float32)
+    check(b, a, B)
+
+
 def test_empty_rows_and_empty_matrix(b):
     a = random_csr(700, 300, 0.05, seed=9)
     keep = np.ones(a.M, bool)
