@@ -47,8 +47,9 @@
 // (drains of one CTA, partial tiles of several) meet in C through red.add on a zeroed C; the pieces of one CTA arrive in
 // program order, those of two CTAs that share a tile in arrival order (run-to-run differences in the last bits of those tiles).
 //
-// Warp roles (480 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer of M block 0, warps 2..9 = builders,
-// warps 10..13 = epilogue (tcgen05.ld 32x32b.x32 -> 16-byte reductions / stores), warp 14 = MMA issuer of M block 1.
+// Warp roles (736 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer of M block 0, warps 2..17 = builders
+// (two lanes per row), warps 18..21 = epilogue (tcgen05.ld 32x32b.x32 -> 16-byte reductions / stores), warp 22 = MMA issuer of
+// M block 1.
 //
 // Semantics that differ from the sparse kernels: a zero of A is multiplied with B, so an Inf/NaN anywhere in B would poison
 // rows that never reference it.  The prepare kernel therefore raises a device flag when B holds a non-finite value (or one
@@ -68,9 +69,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { pipe
 
 constexpr int kTileN = 256, kKC = 16;
 constexpr int kRowsPerCta = 256;                                     // rows of A one CTA builds: two UMMA M blocks of 128
-constexpr int kBuilders = 256, kEpilogue = 128;
+constexpr int kEpilogue = 128;
 constexpr int kIssuers = 2;                                           // MMA-issuing threads: one per M block (accumulator)
-constexpr int kThreads = 64 + kBuilders + kEpilogue + 32;            // the last warp hosts the second issuer
+// LPR = builder threads per row (1, or 2: the entries of a row dealt to two adjacent lanes by parity)
+constexpr int threads_for(int lpr) { return 64 + kRowsPerCta * lpr + kEpilogue + 32; }      // the last warp hosts the second issuer
 constexpr uint32_t kABytes = 32768, kBBytes = 32768;                 // per stage of A (one CTA) / per chunk record of B (256 columns)
 constexpr uint32_t kOffT = 0, kOffP = 16384;                         // tf32 | bf16 pairs inside a stage of A
 constexpr uint32_t kPrefetchChunks = 12;                             // L2 prefetch distance of the B producer, in chunks
@@ -91,7 +93,7 @@ struct Cfg {
     static constexpr uint32_t kAOff = 0;
     static constexpr uint32_t kBOff = kAStages * kABytes;
     static constexpr uint32_t kRingOff = kBOff + kBStages * kBStage;  // [colIdxs | vals][slot 4][row 256][16 B]
-    static constexpr uint32_t kRingBytes = 2 * 4 * kBuilders * 16;
+    static constexpr uint32_t kRingBytes = 2 * 4 * kRowsPerCta * 16;
     static constexpr uint32_t kBarOff = kRingOff + kRingBytes;
     static constexpr uint32_t kNumBars = 2 * kStages + 2;           // full, empty, accum_full, accum_empty
     static constexpr uint32_t kSmemTotal = kBarOff + kNumBars * 8 + 16 + 128;
@@ -303,13 +305,14 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 // NCTA = 2: launched in clusters of two CTAs; blockIdx.x / 2 is the pair, %cluster_ctarank the half.  Only rank 0 issues MMAs.
 //   barriers (same offsets in both CTAs): see full / empty below; accum_full is arrived in BOTH CTAs by the multicast
 //   tcgen05.commit of rank 0; accum_empty lives in rank 0 and collects the epilogue warps of both CTAs.
-template <bool VEC, int NCTA>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool VEC, int NCTA, int LPR>
+__global__ void __launch_bounds__(threads_for(LPR), 1)
 csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
               uint32_t M, uint32_t nnzTotal, const unsigned char *__restrict__ Bt, uint32_t N, float *__restrict__ C, size_t ldc,
               Plan pl, const uint32_t *__restrict__ flag, int vecC) {
     using CF = Cfg<NCTA>;
     constexpr int kStages = CF::kStages, kAStages = kStages;
+    constexpr int kBuilders = kRowsPerCta * LPR, kThreads = threads_for(LPR);
     extern __shared__ __align__(128) unsigned char smem[];
     if (*flag) return;                                        // B holds a non-finite value: the fp32 kernel that follows computes C
     unsigned char *stA = smem + CF::kAOff;
@@ -426,7 +429,11 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
         }
     } else if (warp < 2 + kBuilders / 32) {
         // ---------------------------------------------------------------------------- builders
-        const uint32_t t = threadIdx.x - 64;                  // row this thread builds: M block t / 128, row t % 128 of this CTA's half
+        // Two adjacent lanes share a row: lane half h takes the entries of the row whose index has parity h.  The scatter loop of a
+        // warp is as long as its longest lane; with one thread per row that was ~5.4 iterations per chunk at 10 % density for 1.6
+        // entries on average, and the chunk's operands are complete only when the slowest warp is.
+        const uint32_t bt = threadIdx.x - 64;
+        const uint32_t t = LPR == 2 ? bt >> 1 : bt, h = LPR == 2 ? bt & 1u : 0u;     // t: row this thread builds (M block t / 128, row t % 128)
         const uint32_t mblk = t >> 7, rowInBlk = t & 127;
         const uint32_t offT = kOffT + mblk * 8192 + rowInBlk * 16;
         const uint32_t rowInTile = NCTA == 1 ? t : mblk * 256 + rank * 128 + rowInBlk;
@@ -435,71 +442,84 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
         uint32_t s = 0, round = 0;
         while (seg.next(tile, kb, ke)) {
             const uint32_t r = (tile / pl.tilesN) * CF::kTileM + rowInTile;
-            uint32_t p = 0, end = 0;
+            uint32_t p0 = 0, end = 0;
             if (r < M) {
-                p = __ldg(rowPtrs + r);
+                p0 = __ldg(rowPtrs + r);
                 end = __ldg(rowPtrs + r + 1);
                 if (kb > 0) {                                 // first entry of the row at or after column 16 kb
                     const uint32_t target = kb * kKC;
-                    uint32_t lo = p, hi = end;
+                    uint32_t lo = p0, hi = end;
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
                         if (__ldg(colIdxs + mid) < target) lo = mid + 1; else hi = mid;
                     }
-                    p = lo;
+                    p0 = lo;
                 }
             }
-            // Entries reach the thread through a ring in shared memory: 4 slots of 4 entries (16 B of colIdxs + 16 B of vals) per
-            // row, filled with cp.async.  (A register FIFO filled with ordinary loads does not work here: the scoreboard is
-            // per warp and register, so a lane shifting its FIFO waits for the load another lane issued a moment ago -- ncu on the
-            // first version: 29 % of all samples on that move, one exposed memory latency per chunk.)  Refills are issued at the
-            // start of a chunk, one commit group per chunk, and cp.async.wait_group 2 makes the groups older than two chunks
-            // visible: a block is requested 12..16 entries before it is read.  Entry p of the row lives at
-            // ring + (p / 4 % 4) * 4096 + (p % 4) * 4.
-            uint32_t fb = p & ~3u;                            // next block to request
+            uint32_t p = LPR == 2 ? p0 + ((h - p0) & 1u) : p0;   // this lane's next entry
+            // Entries reach the lanes through a ring in shared memory: 4 slots of 4 entries (16 B of colIdxs + 16 B of vals) per
+            // row, filled with cp.async by the even lane.  (A register FIFO filled with ordinary loads does not work here: the
+            // scoreboard is per warp and register, so a lane shifting its FIFO waits for the load another lane issued a moment ago
+            // -- ncu on the first version: 29 % of all samples on that move, one exposed memory latency per chunk.)  Refills are
+            // issued at the start of a chunk, one commit group per chunk, and cp.async.wait_group 2 (+ __syncwarp for the odd
+            // lane) makes the groups older than two chunks visible: a block is requested 12..16 entries before it is read.
+            // Entry p of the row lives at ring + (p / 4 % 4) * 4096 + (p % 4) * 4.  Both lanes track fb / lb identically.
+            uint32_t fb = p0 & ~3u;                           // next block to request
             uint32_t lb = fb;                                 // entries below lb have landed
-            auto refill = [&]() {
-                uint32_t lim = (p & ~3u) + 16u;
+            auto refill = [&](uint32_t plow) {                // plow: the lower of the two lanes' next entries
+                uint32_t lim = (plow & ~3u) + 16u;
                 if (lim > end) lim = end;
                 while (fb < lim) {
-                    const uint32_t dst = ring + ((fb & 12u) << 10);
-                    if (VEC) {
-                        const uint32_t valid = (nnzTotal - fb < 4u ? nnzTotal - fb : 4u) * 4u;
-                        cp_async16(dst, colIdxs + fb, valid);
-                        cp_async16(dst + 16384u, vals + fb, valid);
-                    } else {
+                    if (h == 0) {
+                        const uint32_t dst = ring + ((fb & 12u) << 10);
+                        if (VEC) {
+                            const uint32_t valid = (nnzTotal - fb < 4u ? nnzTotal - fb : 4u) * 4u;
+                            cp_async16(dst, colIdxs + fb, valid);
+                            cp_async16(dst + 16384u, vals + fb, valid);
+                        } else {
 #pragma unroll
-                        for (uint32_t e = 0; e < 4; ++e) {
-                            const bool in = fb + e < nnzTotal;
-                            cp_async4(dst + 4 * e, colIdxs + (in ? fb + e : fb), in ? 4u : 0u);
-                            cp_async4(dst + 16384u + 4 * e, vals + (in ? fb + e : fb), in ? 4u : 0u);
+                            for (uint32_t e = 0; e < 4; ++e) {
+                                const bool in = fb + e < nnzTotal;
+                                cp_async4(dst + 4 * e, colIdxs + (in ? fb + e : fb), in ? 4u : 0u);
+                                cp_async4(dst + 16384u + 4 * e, vals + (in ? fb + e : fb), in ? 4u : 0u);
+                            }
                         }
                     }
                     fb += 4;
                 }
             };
+            auto lower_of_pair = [&]() {
+                if constexpr (LPR == 1) return p;
+                const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, p, 1);
+                return o < p ? o : p;
+            };
 
             // (Two chunks per builder pass -- amortising the chain barrier wake-up -> clears -> LDS -> stores -> proxy fence -> arrive
-            //  over 32 columns -- was measured and is slower from 10 % density: 2.61 vs 2.52 ms, 7.5 vs 6.4 ms at 50 %: the scatter
-            //  loop of a pass is as long as its longest row, and the issuer waits for the whole pass.)
+            //  over 32 columns -- was measured and is slower from 10 % density: 2.61 vs 2.52 ms, 7.5 vs 6.4 ms at 50 %.  Also dropped:
+            //  keeping the (column, value) of the next entry in registers across chunks and issuing its ring loads before the current
+            //  entry's stores: 2.65 vs 2.50 ms at 10 %.)
             uint32_t fbPrev = fb;                             // fb before the refill of the previous chunk
-            // (Also measured and dropped: keeping the (column, value) of entry p in registers across chunks and issuing the next
-            //  entry's ring loads before the current one's stores -- 2.65 vs 2.50 ms at 10 %: the extra state costs more than the
-            //  shared-memory round trip it hides.)
             for (uint32_t k = kb; k < ke; ++k) {
                 const uint32_t fbBefore = fb;
-                refill();
+                refill(lower_of_pair());
                 asm volatile("cp.async.commit_group;" ::: "memory");
                 if (k == kb) { asm volatile("cp.async.wait_group 0;" ::: "memory"); lb = fb; }
                 else {                                        // all groups but the last two have landed: requested >= 2 chunks ago
                     asm volatile("cp.async.wait_group 2;" ::: "memory");
                     if (fbPrev > lb) lb = fbPrev;
                 }
+                if constexpr (LPR == 2) __syncwarp();         // the even lane's copies are visible to the odd lane
                 fbPrev = fbBefore;
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
                 const uint32_t aT = stA32 + s * kABytes + offT;
+                if constexpr (LPR == 2) {                     // each lane clears half of the row: k groups 2h, 2h + 1 of both operand tiles
+                    sts_zero16(aT + (2 * h) * 2048); sts_zero16(aT + (2 * h + 1) * 2048);
+                    sts_zero16(aT + kOffP + (2 * h) * 2048); sts_zero16(aT + kOffP + (2 * h + 1) * 2048);
+                    __syncwarp();                             // ... before the partner may store into them
+                } else {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) { sts_zero16(aT + g * 2048); sts_zero16(aT + kOffP + g * 2048); }
+                    for (int g = 0; g < 4; ++g) { sts_zero16(aT + g * 2048); sts_zero16(aT + kOffP + g * 2048); }
+                }
                 const uint32_t k0 = k * kKC;
                 for (;;) {
                     const uint32_t stop = end < lb ? end : lb;
@@ -529,12 +549,17 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                         const uint32_t dstT = aT + ((kk & 12u) << 9) + ((kk & 3u) << 2);
                         sts_u32(dstT, tb);
                         sts_u32(dstT + kOffP, pk);
-                        ++p;
+                        p += LPR;
                     }
-                    if (done || p >= end) break;
-                    // the row has more entries, but they are not known to have landed (a chunk that used more than ~2 blocks)
-                    if (p >= fb) { refill(); asm volatile("cp.async.commit_group;" ::: "memory"); }
+                    // a lane whose row has more entries that are not known to have landed (a chunk that used more than ~2 blocks)
+                    // needs the whole warp: the even lanes own the copies
+                    const bool need = !done && p < end;
+                    if constexpr (LPR == 2) { if (!__any_sync(0xFFFFFFFFu, need)) break; }
+                    else { if (!need) break; }
+                    refill(lower_of_pair());
+                    asm volatile("cp.async.commit_group;" ::: "memory");
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    if constexpr (LPR == 2) __syncwarp();
                     lb = fb;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core (async proxy) reads
@@ -544,7 +569,7 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
             }
         }
     } else {     // (the issuer warps were taken by the branch above)
-        // ---------------------------------------------------------------------------- epilogue (warps 10..13)
+        // ---------------------------------------------------------------------------- epilogue (warps 18..21)
         // TMEM lanes [32 q, 32 q + 32) are the ones this warp may read; it drains both M blocks of those lanes.  Every piece is
         // added to C (zeroed by the launcher) with red.global.add.v4.f32; a tile that is one single piece is stored.
         // (Load-add-store by the CTA that owns a tile was 3x slower than red.add: the C tile does not stay in L2 between two
@@ -725,11 +750,16 @@ static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float 
         }
         const bool vecA = ((reinterpret_cast<uintptr_t>(colIdxs) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
         const int vecC = (N % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-        auto kern = vecA ? csr_tc_kernel<true, NCTA> : csr_tc_kernel<false, NCTA>;
+        // builder threads per row: two lanes per row pay from ~12 % density (25605^2 x 512: 50 %: 6.48 -> 4.79 ms, 10 %: 2.50 = 2.50,
+        // 5 %: 2.16 -> 2.26, 2 %: 1.89 -> 2.10: below that the second set of warps only adds fixed work per chunk)
+        static const int lprEnv = getenv("CUSPMM_TC_LPR") ? atoi(getenv("CUSPMM_TC_LPR")) : 0;          // tuning hook
+        const int lpr = lprEnv == 1 || lprEnv == 2 ? lprEnv : ((double)nnz >= 0.12 * (double)M * (double)K ? 2 : 1);
+        auto kern = lpr == 2 ? (vecA ? csr_tc_kernel<true, NCTA, 2> : csr_tc_kernel<false, NCTA, 2>)
+                             : (vecA ? csr_tc_kernel<true, NCTA, 1> : csr_tc_kernel<false, NCTA, 1>);
         if (set_smem_once(kern, CF::kSmemTotal) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "cannot reserve %u bytes of shared memory", CF::kSmemTotal); break; }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(pl.grid * NCTA, 1, 1);
-        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.blockDim = dim3(threads_for(lpr), 1, 1);
         cfg.dynamicSmemBytes = CF::kSmemTotal;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
