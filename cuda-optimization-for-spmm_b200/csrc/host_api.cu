@@ -460,7 +460,10 @@ extern "C" int cuspmm_spmm_bsr_host(const uint32_t *blockRowPtrs, const uint32_t
     return rc;
 }
 
+namespace cuspmm_b200 { void tc_pool_trim(int dev); }       // spmm_csr_tc.cu: the pools of the tiled copies of B
+
 extern "C" int cuspmm_host_pipeline_release(int device) {
+    cuspmm_b200::tc_pool_trim(device);
     std::lock_guard<std::mutex> lock(g_pipes_mu);
     int cur = 0;
     cudaGetDevice(&cur);

@@ -673,9 +673,17 @@ csr_tc_fallback_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__r
 
 // one memory pool per device for the tiled copy of B: stream-ordered (cudaMallocAsync / cudaFreeAsync on the caller's stream), so
 // concurrent calls on different streams never share a buffer and nothing synchronises; the pool keeps what it has allocated
+static std::mutex g_tc_pool_mu;
+static cudaMemPool_t g_tc_pools[64] = {};
+// gives the memory the pools hold back to the device (cuspmm_host_pipeline_release); device < 0: all
+void tc_pool_trim(int dev) {
+    std::lock_guard<std::mutex> lock(g_tc_pool_mu);
+    for (int d = 0; d < 64; ++d)
+        if (g_tc_pools[d] && (dev < 0 || dev == d)) cudaMemPoolTrimTo(g_tc_pools[d], 0);
+}
 static cudaMemPool_t tc_pool(int dev) {
-    static std::mutex mu;
-    static cudaMemPool_t pools[64] = {};
+    std::mutex &mu = g_tc_pool_mu;
+    cudaMemPool_t *pools = g_tc_pools;
     std::lock_guard<std::mutex> lock(mu);
     if (dev < 0 || dev >= 64) return nullptr;
     if (!pools[dev]) {

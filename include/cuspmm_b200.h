@@ -229,7 +229,8 @@ int cuspmm_csr_check_sorted(const uint32_t *rowPtrs_dev, const uint32_t *colIdxs
  * kernels.  Host buffers should be pinned (cudaHostAlloc / cuspmm_host_alloc) for the copies to be asynchronous.
  * Synchronises before returning, on every exit path.  `device_ms` (optional) receives the device time of the whole
  * pipeline measured with CUDA events.  Device staging buffers are cached per device between calls and freed by
- * cuspmm_host_pipeline_release(device) (device < 0: all devices).  CSR / ELL: column indices ascending inside a row. */
+ * cuspmm_host_pipeline_release(device) (device < 0: all devices), which also trims the stream-ordered pools CSR variant 8 keeps
+ * for its per-call copy of B.  CSR / ELL: column indices ascending inside a row. */
 int cuspmm_spmm_csr_host(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals,
                          uint32_t M, uint32_t K, uint32_t nnz,
                          const float *B, uint32_t N, float *C, int variant, float *device_ms);
