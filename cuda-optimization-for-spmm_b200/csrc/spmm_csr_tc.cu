@@ -18,9 +18,11 @@
 // Accumulation.  tcgen05.mma does not round its fp32 accumulator to nearest: it truncates.  Every MMA step loses on average
 // 2^-25.5 of |accumulator| TOWARDS ZERO -- a bias, not noise: after the 6400 steps of K = 25605 the first version was 1.2e-5
 // of sum|a||b| off (7.7e-3 absolute on |C| ~ 20), outside the tolerance.  So the accumulators are drained into C every
-// kFlushChunks = 64 chunks (256 steps: bias <= 5e-6 of |partial sum| even when all terms have one sign) with
-// red.global.add.v4.f32, whose additions round to nearest, and start over from zero.  A drain costs ~18 000 clocks (the LSU
-// retires about one reduction lane per 1.3 clocks): +12 % at 64 chunks.
+// kFlushChunks = 64 chunks (256 steps: bias <= 5e-6 of |partial sum| even when all terms have one sign) by reductions that
+// round to nearest in L2, and start over from zero.  Drain path: TMEM -> registers -> a swizzled 4 KB staging tile per epilogue
+// warp -> cp.reduce.async.bulk.tensor (.add) -- ~8 000 clocks per drain; the first form, red.global.add.v4.f32 straight from
+// registers, cost ~20 000 (the LSU retires about one reduction lane per 1.3 clocks) and is kept for a C that a tensor map
+// cannot describe (unaligned, odd pitch) and for the one-CTA-per-tile hook.
 //
 // Data layout.  UMMA operands are K-major without swizzle: "core matrices" of 8 rows x 16 bytes, contiguous (128 B);
 // element (row, k) of a tf32 operand lives at [k / 4][row][k % 4], of a bf16 operand at [k / 8][row][k % 8].
@@ -44,7 +46,7 @@
 //
 // Decomposition.  The work of a tile does not depend on its non-zeros, so tiles are spread over a persistent grid of one CTA
 // per SM: floor(tiles / grid) whole tiles per CTA, the remaining tiles cut into equal runs of chunks ("stream-K").  All pieces
-// (drains of one CTA, partial tiles of several) meet in C through red.add on a zeroed C; the pieces of one CTA arrive in
+// (drains of one CTA, partial tiles of several) meet in C through reductions on a zeroed C; the pieces of one CTA arrive in
 // program order, those of two CTAs that share a tile in arrival order (run-to-run differences in the last bits of those tiles).
 //
 // Warp roles (736 threads): warp 0 = TMA producer for B, warp 1 = TMEM allocator + MMA issuer of M block 0, warps 2..17 = builders
@@ -85,18 +87,23 @@ template <int NCTA>
 struct Cfg {
     // the builders need more than one chunk time (clear, scatter, proxy fence, arrive): with 3 stages the issuer found the
     // next chunk's A late by ~150 clocks every chunk.  A pair has the room for 4 (its B stages are half as large).
-    static constexpr int kStages = NCTA == 1 ? 3 : 4;
-    static constexpr int kAStages = kStages, kBStages = kStages;
+    static constexpr int kStages = NCTA == 1 ? 3 : 4;                 // stages of A = barriers (indexed by chunk % kStages)
+    static constexpr int kAStages = kStages;
+    static constexpr int kBStages = 3;                                // buffers of B (chunk % 3): TMA needs no builder latency covered
     static constexpr uint32_t kBStage = kBBytes / NCTA;               // bytes of a B chunk one CTA holds: [b_t | pairs]
     static constexpr uint32_t kBOffP = kBStage / 2;
     static constexpr uint32_t kBLbo = (kTileN / NCTA) * 16;           // next k group of the B operand
     static constexpr uint32_t kAOff = 0;
     static constexpr uint32_t kBOff = kAStages * kABytes;
-    static constexpr uint32_t kRingOff = kBOff + kBStages * kBStage;  // [colIdxs | vals][slot 4][row 256][16 B]
+    // pairs: 4 x 4 KB staging tiles (32 rows x 32 columns, 128-byte swizzle) for the accumulator drains through TMA reductions
+    static constexpr uint32_t kOutOff = kBOff + kBStages * kBStage;
+    static constexpr uint32_t kOutBytes = NCTA == 2 ? 4 * 4096 : 0;
+    static constexpr uint32_t kRingOff = kOutOff + kOutBytes;         // [colIdxs | vals][slot 4][row 256][16 B]
     static constexpr uint32_t kRingBytes = 2 * 4 * kRowsPerCta * 16;
     static constexpr uint32_t kBarOff = kRingOff + kRingBytes;
     static constexpr uint32_t kNumBars = 2 * kStages + 2;           // full, empty, accum_full, accum_empty
     static constexpr uint32_t kSmemTotal = kBarOff + kNumBars * 8 + 16 + 128;
+    static_assert(kOutOff % 1024 == 0, "the staging tiles are addressed with the 128-byte swizzle pattern (1024-byte period)");
     static constexpr int kTileM = kRowsPerCta * NCTA;
     static_assert(kSmemTotal <= 232448, "more than 227 KB of shared memory");
 };
@@ -309,7 +316,7 @@ template <bool VEC, int NCTA, int LPR>
 __global__ void __launch_bounds__(threads_for(LPR), 1)
 csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
               uint32_t M, uint32_t nnzTotal, const unsigned char *__restrict__ Bt, uint32_t N, float *__restrict__ C, size_t ldc,
-              Plan pl, const uint32_t *__restrict__ flag, int vecC) {
+              Plan pl, const uint32_t *__restrict__ flag, int vecC, const __grid_constant__ CUtensorMap tmapC, int tmaDrain) {
     using CF = Cfg<NCTA>;
     constexpr int kStages = CF::kStages, kAStages = kStages;
     constexpr int kBuilders = kRowsPerCta * LPR, kThreads = threads_for(LPR);
@@ -365,18 +372,23 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
     if (warp == 0) {
         // ---------------------------------------------------------------------------- B producer (this CTA's part of every chunk)
         if (lane == 0) {
-            uint32_t s = 0, round = 0;                        // ring slot, times the ring has wrapped
+            // chunk u (counted over the whole CTA) lands in buffer u % 3 and completes barrier full[u % kStages]; the buffer is
+            // free once the MMAs of chunk u - 3 are done = phase of empty[(u - 3) % kStages]
+            uint32_t u = 0, sb = 0;
             while (seg.next(tile, kb, ke)) {
                 const uint32_t ct = tile % pl.tilesN;
                 const unsigned char *src = Bt + ((size_t)ct * pl.chunks + kb) * kBBytes + rank * CF::kBStage;
-                for (uint32_t k = kb; k < ke; ++k, src += kBBytes) {
+                for (uint32_t k = kb; k < ke; ++k, ++u, src += kBBytes) {
                     // the records of the next chunks are pulled into L2 well ahead of the copy into shared memory
                     if (k + kPrefetchChunks < pl.chunks)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)kPrefetchChunks * kBBytes), "r"(CF::kBStage) : "memory");
-                    if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
-                    mbar_expect_tx(full + s, CF::kBStage);
-                    bulk_g2s(stB + s * CF::kBStage, src, CF::kBStage, full + s);
-                    if (++s == kStages) { s = 0; ++round; }
+                    if (u >= (uint32_t)CF::kBStages) {
+                        const uint32_t w = u - CF::kBStages;
+                        mbar_wait(empty + w % kStages, (w / kStages) & 1);
+                    }
+                    mbar_expect_tx(full + u % kStages, CF::kBStage);
+                    bulk_g2s(stB + sb * CF::kBStage, src, CF::kBStage, full + u % kStages);
+                    if (++sb == (uint32_t)CF::kBStages) sb = 0;
                 }
             }
         }
@@ -386,20 +398,33 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
             // ------------------------------------------------------------------------ MMA issuer of M block m
             constexpr uint32_t idT = make_idesc(2, 128 * NCTA, kTileN), idH = make_idesc(1, 128 * NCTA, kTileN);
             const uint32_t d = tmem_base + m * kTileN;
-            uint32_t sa = 0, roundA = 0, pieces = 0;
+            uint32_t sa = 0, roundA = 0, sb = 0, pieces = 0;
             bool ready = false;                               // the operands of the chunk about to be issued were seen complete already
+#ifdef CUSPMM_TC_DEBUG
+            long long dbgW = 0, dbgD = 0, dbgN = 0, dbgR = 0;
+            const long long dbgT0 = clock64();
+#endif
             while (seg.next(tile, kb, ke)) {
                 for (uint32_t k = kb; k < ke; ++k) {
                     const bool first = (k - kb) % F == 0;     // first chunk of a piece: the accumulator starts over
+#ifdef CUSPMM_TC_DEBUG
+                    const long long t0 = clock64();
+#endif
                     if (first && pieces > 0) {
                         if constexpr (NCTA == 1) mbar_wait(accum_empty, (pieces - 1) & 1); else mbar_wait_cluster(accum_empty, (pieces - 1) & 1);
                         tc_fence_after();
                     }
+#ifdef CUSPMM_TC_DEBUG
+                    const long long t1 = clock64();
+#endif
                     if (!ready) {
                         if constexpr (NCTA == 1) mbar_wait(full + sa, roundA & 1); else mbar_wait_cluster(full + sa, roundA & 1);
                     }
+#ifdef CUSPMM_TC_DEBUG
+                    dbgD += t1 - t0; dbgW += clock64() - t1; ++dbgN; dbgR += ready;
+#endif
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(stA + sa * kABytes) + m * 8192, b0 = smem_u32(stB + sa * CF::kBStage);
+                    const uint32_t a0 = smem_u32(stA + sa * kABytes) + m * 8192, b0 = smem_u32(stB + sb * CF::kBStage);
                     // Operand tiles hold 4 k-groups of 4 k: a tf32 MMA (K = 8) and a pair MMA (K = 16 = 8 k x 2) both take two of
                     // them.  A (M = 128 rows per CTA): next k group 2048 B; B (N = 256 columns, 128 per CTA of a pair): kBLbo; next 8
                     // rows / columns 128 B
@@ -410,12 +435,18 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                     umma_bf16<NCTA>(d, make_desc(a0 + kOffP + 4096, 2048, 128), make_desc(b0 + CF::kBOffP + 2 * CF::kBLbo, CF::kBLbo, 128), idH);
                     umma_commit<NCTA>(empty + sa);            // (with the other issuer's commit) the stage may be refilled
                     if (++sa == kStages) { sa = 0; ++roundA; }
+                    if (++sb == (uint32_t)CF::kBStages) sb = 0;
                     if ((k + 1 - kb) % F == 0 || k + 1 == ke) { umma_commit<NCTA>(accum_full); ++pieces; }
                     // The tensor pipe is still busy with what was just queued: look at the barrier of the NEXT chunk now (one
                     // non-blocking test), so that its latency is not paid after the queue has run dry.
                     if constexpr (NCTA == 1) ready = mbar_test(full + sa, roundA & 1); else ready = mbar_test_cluster(full + sa, roundA & 1);
                 }
             }
+#ifdef CUSPMM_TC_DEBUG
+            if (unit == 0 || unit == 37)
+                printf("unit %u issuer %u: %lld chunks (%lld ready early), %lld clk per chunk; waited per chunk: operands %lld, drain %lld\n",
+                       unit, m, dbgN, dbgR, (clock64() - dbgT0) / dbgN, dbgW / dbgN, dbgD / dbgN);
+#endif
         } else if (NCTA == 2 && lane == 0 && m == 0) {
             // ------------------------------------------------------------------------ rank 1: tell rank 0 when this half is ready
             uint32_t sa = 0, roundA = 0;
@@ -576,6 +607,60 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
         //  drains and the loads are serialised behind the TMEM reads -- 59 000 clocks per drain against 18 000.)
         const uint32_t q = warp & 3;
         uint32_t pieces = 0;
+        if (NCTA == 2 && tmaDrain) {
+            // Drain through the TMA: 32 rows x 32 columns of an accumulator go TMEM -> registers -> a 4 KB staging tile of this warp
+            // (128-byte swizzle: lane = row writes its eight 16-byte pieces to piece ^ (row % 8), no bank conflicts) -> ONE
+            // cp.reduce.async.bulk.tensor (.add, fp32: round-to-nearest adds in L2, rows / columns past the end of C clipped by the
+            // tensor map).  The red.add path below pushes every 16 bytes through the LSU (~1.3 clocks per lane: ~20 000 clocks per
+            // drain, a fifth of the kernel); here the LSU only sees the shared-memory stores.
+            const uint32_t stage = smem_u32(smem + CF::kOutOff) + (warp - (2 + kBuilders / 32)) * 4096u;
+            const uint32_t myrow = stage + lane * 128u;
+            while (seg.next(tile, kb, ke)) {
+                const uint32_t rt = tile / pl.tilesN, ct = tile % pl.tilesN;
+                for (uint32_t k = kb; k < ke; k += F, ++pieces) {
+                    mbar_wait(accum_full, pieces & 1);
+                    tc_fence_after();
+#pragma unroll 1
+                    for (uint32_t em = 0; em < 2; ++em) {
+                        const uint32_t row0 = rt * CF::kTileM + em * 256 + rank * 128 + q * 32;
+#pragma unroll 1
+                        for (uint32_t cb = 0; cb < kTileN / 32; ++cb) {
+                            uint32_t v[32];
+                            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + em * kTileN + cb * 32;
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                                         "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                         : "r"(taddr));
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            // the previous reduction of this warp has read the staging tile
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+#pragma unroll
+                            for (uint32_t j = 0; j < 8; ++j)
+                                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};"
+                                             ::"r"(myrow + ((j ^ (lane & 7u)) << 4)), "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0 && row0 < M && ct * kTileN + cb * 32 < N) {
+                                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                             ::"l"(&tmapC), "r"(ct * kTileN + cb * 32), "r"(row0), "r"(stage) : "memory");
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                        }
+                    }
+                    // the accumulators have been read: the next piece may start (the reductions complete on their own)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (rank == 0) mbar_arrive(accum_empty); else mbar_arrive_remote(accum_empty, 0);
+                    }
+                }
+            }
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all of this warp's reductions have been performed
+        } else
         while (seg.next(tile, kb, ke)) {
             const uint32_t rt = tile / pl.tilesN, ct = tile % pl.tilesN;
             const bool direct = (kb == 0 && ke == pl.chunks && pl.chunks <= F);     // the only piece of the tile: plain stores
@@ -750,8 +835,25 @@ static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float 
         csr_tc_prepare_B<NCTA><<<dim3(2 * pl.chunks, pl.tilesN), 256, 0, st>>>(B, K, N, ldb, ws, pl.chunks, flag);
         if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_prepare_B failed"); break; }
         count_launch();
-        // every tile is drained into C piece by piece with red.add (only a tile that is a single piece is stored): C starts at zero
-        const bool allDirect = pl.chunks <= pl.flushChunks && (pl.remTiles == 0 || pl.unitsPerCta % pl.chunks == 0);
+        // accumulator drains through TMA reductions (pairs; C 16-byte aligned with a 16-byte multiple as row pitch): a tensor map of
+        // C with 32 x 32 boxes and the 128-byte swizzle the epilogue writes its staging tiles in
+        CUtensorMap tmapC;
+        memset(&tmapC, 0, sizeof tmapC);
+        static const int tmaEnv = getenv("CUSPMM_TC_TMA_DRAIN") ? atoi(getenv("CUSPMM_TC_TMA_DRAIN")) : 1;   // tuning hook
+        int tmaDrain = 0;
+        if (NCTA == 2 && tmaEnv && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc * sizeof(float)) % 16 == 0) {
+            tmemk::EncodeTiledFn encode = tmemk::tensor_map_encoder();
+            const cuuint64_t dims[2] = {N, M};
+            const cuuint64_t strides[1] = {(cuuint64_t)ldc * sizeof(float)};
+            const cuuint32_t box[2] = {32, 32};
+            const cuuint32_t estr[2] = {1, 1};
+            if (encode && encode(&tmapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                tmaDrain = 1;
+        }
+        // every tile is drained into C piece by piece with reductions (on the red.add path a tile that is a single piece is stored):
+        // C starts at zero
+        const bool allDirect = !tmaDrain && pl.chunks <= pl.flushChunks && (pl.remTiles == 0 || pl.unitsPerCta % pl.chunks == 0);
         if (!allDirect && cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st) != cudaSuccess) {
             rc = set_error(CUSPMM_ERR_CUDA, "memset of C failed");
             break;
@@ -779,7 +881,7 @@ static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float 
         cfg.numAttrs = 1;
         const unsigned char *wsc = ws;
         const uint32_t *flagc = flag;
-        if (cudaLaunchKernelEx(&cfg, kern, rowPtrs, colIdxs, vals, M, nnz, wsc, N, C, ldc, pl, flagc, vecC) != cudaSuccess) {
+        if (cudaLaunchKernelEx(&cfg, kern, rowPtrs, colIdxs, vals, M, nnz, wsc, N, C, ldc, pl, flagc, vecC, tmapC, tmaDrain) != cudaSuccess) {
             rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_kernel failed: %s", cudaGetErrorString(cudaPeekAtLastError()));
             break;
         }
