@@ -471,6 +471,9 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
         const uint32_t ring = smem_u32(smem + CF::kRingOff) + t * 16u;   // this row's slot 0 of the colIdxs ring; vals 16 KB further
         const uint32_t stA32 = smem_u32(stA);
         uint32_t s = 0, round = 0;
+#ifdef CUSPMM_TC_DEBUG
+        long long dbgRefill = 0, dbgWaitE = 0, dbgZero = 0, dbgLoop = 0, dbgFence = 0, dbgCh = 0;
+#endif
         while (seg.next(tile, kb, ke)) {
             const uint32_t r = (tile / pl.tilesN) * CF::kTileM + rowInTile;
             uint32_t p0 = 0, end = 0;
@@ -531,6 +534,9 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
             //  entry's stores: 2.65 vs 2.50 ms at 10 %.)
             uint32_t fbPrev = fb;                             // fb before the refill of the previous chunk
             for (uint32_t k = kb; k < ke; ++k) {
+#ifdef CUSPMM_TC_DEBUG
+                const long long tb0 = clock64();
+#endif
                 const uint32_t fbBefore = fb;
                 refill(lower_of_pair());
                 asm volatile("cp.async.commit_group;" ::: "memory");
@@ -541,7 +547,13 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                 }
                 if constexpr (LPR == 2) __syncwarp();         // the even lane's copies are visible to the odd lane
                 fbPrev = fbBefore;
+#ifdef CUSPMM_TC_DEBUG
+                const long long tb1 = clock64();
+#endif
                 if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+#ifdef CUSPMM_TC_DEBUG
+                const long long tb2 = clock64();
+#endif
                 const uint32_t aT = stA32 + s * kABytes + offT;
                 if constexpr (LPR == 2) {                     // each lane clears half of the row: k groups 2h, 2h + 1 of both operand tiles
                     sts_zero16(aT + (2 * h) * 2048); sts_zero16(aT + (2 * h + 1) * 2048);
@@ -551,16 +563,19 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
 #pragma unroll
                     for (int g = 0; g < 4; ++g) { sts_zero16(aT + g * 2048); sts_zero16(aT + kOffP + g * 2048); }
                 }
+#ifdef CUSPMM_TC_DEBUG
+                const long long tb3 = clock64();
+#endif
                 const uint32_t k0 = k * kKC;
                 for (;;) {
                     const uint32_t stop = end < lb ? end : lb;
                     bool done = false;
-                    while (p < stop) {
-                        const uint32_t ea = ring + ((p & 12u) << 10) + ((p & 3u) << 2);
-                        const uint32_t kk = lds_u32(ea) - k0;                    // columns ascend and are >= k0 here
-                        if (kk >= (uint32_t)kKC) { done = true; break; }
-                        const float v = __uint_as_float(lds_u32(ea + 16384u));
-                        const uint32_t bits = __float_as_uint(v);
+                    // Two entries per round, all four ring loads issued before the first is used: an iteration is a chain of
+                    // shared-memory round trips (~100 clocks each with the pipe loaded by the MMAs: clock64 showed ~220 clocks per
+                    // entry, 1200 of the 1900 clocks a chunk takes at 10 % density), not instructions.  (10 % dense: 2.37 ms with one
+                    // entry per round, 2.23 with two, 2.43 with four (the loads past the chunk are wasted).)
+                    auto place = [&](uint32_t kk, uint32_t bits) {
+                        const float v = __uint_as_float(bits);
                         uint32_t tb = (bits + 0x1000u) & 0xFFFFE000u;          // tf32, round to nearest (ties away)
                         float res = v - __uint_as_float(tb);                   // exact
                         uint32_t pk;                                            // low half bf16(v), high half bf16(res)
@@ -580,6 +595,23 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                         const uint32_t dstT = aT + ((kk & 12u) << 9) + ((kk & 3u) << 2);
                         sts_u32(dstT, tb);
                         sts_u32(dstT + kOffP, pk);
+                    };
+                    while (p < stop) {
+                        const uint32_t q1 = p + LPR;
+                        const bool two = q1 < stop;
+                        const uint32_t ea0 = ring + ((p & 12u) << 10) + ((p & 3u) << 2);
+                        const uint32_t ea1 = ring + ((q1 & 12u) << 10) + ((q1 & 3u) << 2);
+                        const uint32_t c0 = lds_u32(ea0), b0 = lds_u32(ea0 + 16384u);
+                        uint32_t c1 = 0xFFFFFFFFu, b1 = 0u;
+                        if (two) { c1 = lds_u32(ea1); b1 = lds_u32(ea1 + 16384u); }
+                        const uint32_t kk0 = c0 - k0;                            // columns ascend and are >= k0 here
+                        if (kk0 >= (uint32_t)kKC) { done = true; break; }
+                        place(kk0, b0);
+                        p = q1;
+                        if (!two) break;                                          // (p >= stop: the outer logic decides what follows)
+                        const uint32_t kk1 = c1 - k0;
+                        if (kk1 >= (uint32_t)kKC) { done = true; break; }
+                        place(kk1, b1);
                         p += LPR;
                     }
                     // a lane whose row has more entries that are not known to have landed (a chunk that used more than ~2 blocks)
@@ -593,12 +625,23 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                     if constexpr (LPR == 2) __syncwarp();
                     lb = fb;
                 }
+#ifdef CUSPMM_TC_DEBUG
+                const long long tb4 = clock64();
+#endif
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> tensor-core (async proxy) reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full + s);
+#ifdef CUSPMM_TC_DEBUG
+                { const long long tb5 = clock64(); dbgRefill += tb1 - tb0; dbgWaitE += tb2 - tb1; dbgZero += tb3 - tb2; dbgLoop += tb4 - tb3; dbgFence += tb5 - tb4; ++dbgCh; }
+#endif
                 if (++s == kAStages) { s = 0; ++round; }
             }
         }
+#ifdef CUSPMM_TC_DEBUG
+        if (unit == 0 && rank == 0 && lane == 0 && (warp == 2 || warp == 5) && dbgCh)
+            printf("builder warp %u: per chunk: refill+cp.async wait %lld, wait for the stage %lld, clear %lld, scatter loop %lld, fence+arrive %lld\n",
+                   warp, dbgRefill / dbgCh, dbgWaitE / dbgCh, dbgZero / dbgCh, dbgLoop / dbgCh, dbgFence / dbgCh);
+#endif
     } else {     // (the issuer warps were taken by the branch above)
         // ---------------------------------------------------------------------------- epilogue (warps 18..21)
         // TMEM lanes [32 q, 32 q + 32) are the ones this warp may read; it drains both M blocks of those lanes.  Every piece is
