@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CUSPMM_B200_VERSION 200
+#define CUSPMM_B200_VERSION 210
 
 typedef enum {
     CUSPMM_OK = 0,

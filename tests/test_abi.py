@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(L):
 
 
 def test_version_and_error_string(L):
-    assert L.cuspmm_version() == 200
+    assert L.cuspmm_version() == 210
     assert isinstance(L.cuspmm_last_error(), bytes)
 
 
