@@ -749,10 +749,17 @@ namespace cuspmm_b200 { int csr_select_variant(uint32_t M, uint32_t K, uint64_t 
 // chunks): aimed at another GPU's memory that is dozens of round trips of atomics over NVLink per element (measured: 2.5 ms on one
 // GPU, 4.9 ms on eight with the peer-store gather).  Such panels are computed into the panel's own C and sent with one peer copy.
 static bool mgpu_uses_tensor_kernel(cuspmmMgpuPlan pl, const MgpuPanel &q, int variant) {
-    if (pl->fmt != MG_CSR && pl->fmt != MG_COO) return false;
-    if (variant == 8 && pl->fmt == MG_CSR) return true;
-    if (!(variant == 0 || (variant == 2 && pl->fmt == MG_COO))) return false;
-    return cuspmm_b200::csr_select_variant(q.r1 - q.r0, pl->K, q.cnt, pl->N, pl->N % 4 == 0, false) == 8;
+    const bool vok = pl->N % 4 == 0;
+    switch (pl->fmt) {
+    case MG_CSR:
+        return variant == 8 || (variant == 0 && cuspmm_b200::csr_select_variant(q.r1 - q.r0, pl->K, q.cnt, pl->N, vok, false) == 8);
+    case MG_COO:
+        return (variant == 0 || variant == 2) && cuspmm_b200::csr_select_variant(q.r1 - q.r0, pl->K, q.cnt, pl->N, vok, false) == 8;
+    case MG_SELL:
+        return variant == 6 || (variant == 0 && cuspmm_b200::csr_select_variant(q.r1 - q.r0, pl->K, q.cnt, pl->N, vok, true) == 8);
+    default:
+        return false;
+    }
 }
 
 // one multiply of panel q into Cdst on its stream (the current device is q.dev)

@@ -594,8 +594,8 @@ int spmm_rows_quad(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float
 void quad_planned_grid(uint32_t M, uint32_t N, uint64_t *ctas, uint32_t *rows_per_cta);
 // variant 8: A tiles made dense in shared memory, tcgen05.mma with a three-product tf32 / bf16 split (spmm_csr_tc.cu); CSR only
 int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
-                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st);
-bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N);   // is variant 8 expected to beat the fp32 kernels on this shape?
+                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, bool sell, cudaStream_t st);
+bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool sell);   // is variant 8 expected to beat the fp32 kernels?
 // variant 6: nnz split that cuts rows, ordered carry fix-up (spmm_csr_split.cu); needs workspace
 size_t spmm_csr_split_workspace(uint32_t nnz, uint32_t N);
 int spmm_csr_split(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
@@ -636,7 +636,8 @@ static bool tensor_mode_on() {
 
 int csr_select_variant(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool vec_ok, bool sell) {
     if (!vec_ok) return 4;
-    if (!sell && M && K && tensor_mode_on() && tc_kernel_wins(M, K, nnz, N)) return 8;
+    // (on the sliced layout nnz counts slots, padding included: the kernel builds the padding too, as zeros it never stores)
+    if (M && K && tensor_mode_on() && tc_kernel_wins(M, K, nnz, N, sell)) return 8;
     const double density = (double)nnz / ((double)M * (double)K);
     const double per_row = (double)nnz / (double)M;
     // N = 128: one 128-column tile, 31 rows per CTA (N = 256 / 384 would need row-wise TMA copies of 512 bytes: 25605^2,
@@ -741,10 +742,8 @@ static int rows_dispatch(const uint32_t *rowPtrs, const uint32_t *colIdxs, const
             return set_error(CUSPMM_ERR_UNSUPPORTED, "all-TMEM kernel needs N %% 512 == 0 and aligned B/C (N=%u)", N);
         return spmm_rows_quad<SELL>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
     }
-    case 8: {
-        if (SELL) return set_error(CUSPMM_ERR_UNSUPPORTED, "the tensor-core kernel (variant 8) reads CSR, not sliced ELL");
-        return spmm_csr_tc(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, st);
-    }
+    case 8:
+        return spmm_csr_tc(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, SELL, st);
     case 4: {
         dim3 grid(blocks, (N + 127) / 128);
         csr_rowsplit_scalar_kernel<4, SELL><<<grid, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, ipw, B, N, ldb, C, ldc);

@@ -83,11 +83,15 @@ constexpr uint32_t kFlushChunks = 64;                                // 256 accu
 // per tile of 512 rows x 256 columns: each CTA builds its own 256 rows of A but holds only HALF of every B chunk (128 of the
 // 256 columns), so the MMAs read B from shared memory once per 256 rows instead of once per 128, TMA writes half as much, L2
 // delivers half as much, and the space buys rings of 4 + 4 stages instead of 3 + 3.
-template <int NCTA>
+// LPR = 2 is the layout for dense rows (>= 12 % density): two builder lanes per row AND a ring of 8 blocks (32 entries) per row instead
+// of 4 -- a row that uses 8 entries per chunk empties a 16-entry ring faster than the copies land, and every chunk then waits for
+// everything outstanding (50 % dense: 4.4 ms with 4 blocks) -- paid for with one stage of A (3 instead of 4).
+template <int NCTA, int LPR = 1>
 struct Cfg {
     // the builders need more than one chunk time (clear, scatter, proxy fence, arrive): with 3 stages the issuer found the
     // next chunk's A late by ~150 clocks every chunk.  A pair has the room for 4 (its B stages are half as large).
-    static constexpr int kStages = NCTA == 1 ? 3 : 4;                 // stages of A = barriers (indexed by chunk % kStages)
+    static constexpr int kRingBlocks = (NCTA == 2 && LPR == 2) ? 8 : 4;
+    static constexpr int kStages = (NCTA == 1 || LPR == 2) ? 3 : 4;   // stages of A = barriers (indexed by chunk % kStages)
     static constexpr int kAStages = kStages;
     static constexpr int kBStages = 3;                                // buffers of B (chunk % 3): TMA needs no builder latency covered
     static constexpr uint32_t kBStage = kBBytes / NCTA;               // bytes of a B chunk one CTA holds: [b_t | pairs]
@@ -99,7 +103,9 @@ struct Cfg {
     static constexpr uint32_t kOutOff = kBOff + kBStages * kBStage;
     static constexpr uint32_t kOutBytes = NCTA == 2 ? 4 * 4096 : 0;
     static constexpr uint32_t kRingOff = kOutOff + kOutBytes;         // [colIdxs | vals][slot 4][row 256][16 B]
-    static constexpr uint32_t kRingBytes = 2 * 4 * kRowsPerCta * 16;
+    static constexpr uint32_t kRingBytes = 2 * kRingBlocks * kRowsPerCta * 16;
+    static constexpr uint32_t kRingVals = kRingBlocks * kRowsPerCta * 16;       // offset of the values inside the ring
+    static constexpr uint32_t kRingMask = (kRingBlocks - 1) << 2;               // entry index bits that select the block
     static constexpr uint32_t kBarOff = kRingOff + kRingBytes;
     static constexpr uint32_t kNumBars = 2 * kStages + 2;           // full, empty, accum_full, accum_empty
     static constexpr uint32_t kSmemTotal = kBarOff + kNumBars * 8 + 16 + 128;
@@ -312,12 +318,14 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 // NCTA = 2: launched in clusters of two CTAs; blockIdx.x / 2 is the pair, %cluster_ctarank the half.  Only rank 0 issues MMAs.
 //   barriers (same offsets in both CTAs): see full / empty below; accum_full is arrived in BOTH CTAs by the multicast
 //   tcgen05.commit of rank 0; accum_empty lives in rank 0 and collects the epilogue warps of both CTAs.
-template <bool VEC, int NCTA, int LPR>
+// SELL: the rows come from a sliced-ELL matrix (rowPtrs = slicePtrs; entry j of row r at slicePtrs[r / 32] + 32 j + r % 32, padding
+// entries have column 0xFFFFFFFF and end the row): the builder's cursor then counts entries of the row, not positions in colIdxs.
+template <bool VEC, int NCTA, int LPR, bool SELL>
 __global__ void __launch_bounds__(threads_for(LPR), 1)
 csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
               uint32_t M, uint32_t nnzTotal, const unsigned char *__restrict__ Bt, uint32_t N, float *__restrict__ C, size_t ldc,
               Plan pl, const uint32_t *__restrict__ flag, int vecC, const __grid_constant__ CUtensorMap tmapC, int tmaDrain) {
-    using CF = Cfg<NCTA>;
+    using CF = Cfg<NCTA, LPR>;
     constexpr int kStages = CF::kStages, kAStages = kStages;
     constexpr int kBuilders = kRowsPerCta * LPR, kThreads = threads_for(LPR);
     extern __shared__ __align__(128) unsigned char smem[];
@@ -476,16 +484,24 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
 #endif
         while (seg.next(tile, kb, ke)) {
             const uint32_t r = (tile / pl.tilesN) * CF::kTileM + rowInTile;
-            uint32_t p0 = 0, end = 0;
+            // cursor space: CSR -- positions in colIdxs / vals (entry p at address p); sliced ELL -- entries of the row (entry p at
+            // address ebase + 32 p)
+            uint32_t p0 = 0, end = 0, ebase = 0;
             if (r < M) {
-                p0 = __ldg(rowPtrs + r);
-                end = __ldg(rowPtrs + r + 1);
-                if (kb > 0) {                                 // first entry of the row at or after column 16 kb
+                if constexpr (SELL) {
+                    const uint32_t sb = __ldg(rowPtrs + (r >> 5));
+                    ebase = sb + (r & 31u);
+                    end = (__ldg(rowPtrs + (r >> 5) + 1) - sb) >> 5;
+                } else {
+                    p0 = __ldg(rowPtrs + r);
+                    end = __ldg(rowPtrs + r + 1);
+                }
+                if (kb > 0) {                                 // first entry of the row at or after column 16 kb (padding: 0xFFFFFFFF)
                     const uint32_t target = kb * kKC;
                     uint32_t lo = p0, hi = end;
                     while (lo < hi) {
                         const uint32_t mid = (lo + hi) >> 1;
-                        if (__ldg(colIdxs + mid) < target) lo = mid + 1; else hi = mid;
+                        if (__ldg(colIdxs + (SELL ? ebase + 32u * mid : mid)) < target) lo = mid + 1; else hi = mid;
                     }
                     p0 = lo;
                 }
@@ -501,21 +517,29 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
             uint32_t fb = p0 & ~3u;                           // next block to request
             uint32_t lb = fb;                                 // entries below lb have landed
             auto refill = [&](uint32_t plow) {                // plow: the lower of the two lanes' next entries
-                uint32_t lim = (plow & ~3u) + 16u;
+                uint32_t lim = (plow & ~3u) + 4u * CF::kRingBlocks;
                 if (lim > end) lim = end;
                 while (fb < lim) {
                     if (h == 0) {
-                        const uint32_t dst = ring + ((fb & 12u) << 10);
-                        if (VEC) {
+                        const uint32_t dst = ring + ((fb & CF::kRingMask) << 10);
+                        if constexpr (SELL) {
+#pragma unroll
+                            for (uint32_t e = 0; e < 4; ++e) {
+                                const bool in = fb + e < end;
+                                const size_t at = (size_t)ebase + 32u * (size_t)(in ? fb + e : fb);
+                                cp_async4(dst + 4 * e, colIdxs + at, in ? 4u : 0u);
+                                cp_async4(dst + CF::kRingVals + 4 * e, vals + at, in ? 4u : 0u);
+                            }
+                        } else if (VEC) {
                             const uint32_t valid = (nnzTotal - fb < 4u ? nnzTotal - fb : 4u) * 4u;
                             cp_async16(dst, colIdxs + fb, valid);
-                            cp_async16(dst + 16384u, vals + fb, valid);
+                            cp_async16(dst + CF::kRingVals, vals + fb, valid);
                         } else {
 #pragma unroll
                             for (uint32_t e = 0; e < 4; ++e) {
                                 const bool in = fb + e < nnzTotal;
                                 cp_async4(dst + 4 * e, colIdxs + (in ? fb + e : fb), in ? 4u : 0u);
-                                cp_async4(dst + 16384u + 4 * e, vals + (in ? fb + e : fb), in ? 4u : 0u);
+                                cp_async4(dst + CF::kRingVals + 4 * e, vals + (in ? fb + e : fb), in ? 4u : 0u);
                             }
                         }
                     }
@@ -599,11 +623,11 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
                     while (p < stop) {
                         const uint32_t q1 = p + LPR;
                         const bool two = q1 < stop;
-                        const uint32_t ea0 = ring + ((p & 12u) << 10) + ((p & 3u) << 2);
-                        const uint32_t ea1 = ring + ((q1 & 12u) << 10) + ((q1 & 3u) << 2);
-                        const uint32_t c0 = lds_u32(ea0), b0 = lds_u32(ea0 + 16384u);
+                        const uint32_t ea0 = ring + ((p & CF::kRingMask) << 10) + ((p & 3u) << 2);
+                        const uint32_t ea1 = ring + ((q1 & CF::kRingMask) << 10) + ((q1 & 3u) << 2);
+                        const uint32_t c0 = lds_u32(ea0), b0 = lds_u32(ea0 + CF::kRingVals);
                         uint32_t c1 = 0xFFFFFFFFu, b1 = 0u;
-                        if (two) { c1 = lds_u32(ea1); b1 = lds_u32(ea1 + 16384u); }
+                        if (two) { c1 = lds_u32(ea1); b1 = lds_u32(ea1 + CF::kRingVals); }
                         const uint32_t kk0 = c0 - k0;                            // columns ascend and are >= k0 here
                         if (kk0 >= (uint32_t)kKC) { done = true; break; }
                         place(kk0, b0);
@@ -775,6 +799,7 @@ csr_tc_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__
 
 // The kernel that computes C when B holds non-finite values (it exits at once otherwise): plain fp32, a warp per row, lanes over
 // the columns.  Only stored entries are multiplied, as in the reference; speed does not matter here.
+template <bool SELL>
 __global__ void __launch_bounds__(256)
 csr_tc_fallback_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals,
                        uint32_t M, const float *__restrict__ B, uint32_t N, size_t ldb, float *__restrict__ C, size_t ldc,
@@ -782,25 +807,37 @@ csr_tc_fallback_kernel(const uint32_t *__restrict__ rowPtrs, const uint32_t *__r
     if (!*onlyIf) return;
     const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
     for (uint32_t r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < M; r += warpsPerGrid) {
-        const uint32_t p0 = rowPtrs[r], p1 = rowPtrs[r + 1];
+        // CSR: entries p0 .. p1 - 1; sliced ELL: entry j at first + 32 j, the row ends at its first padding entry
+        size_t first;
+        uint32_t len, stride;
+        if constexpr (SELL) {
+            const uint32_t sb = rowPtrs[r >> 5];
+            first = (size_t)sb + (r & 31u);
+            len = (rowPtrs[(r >> 5) + 1] - sb) >> 5;
+            stride = 32;
+        } else {
+            first = rowPtrs[r];
+            len = rowPtrs[r + 1] - rowPtrs[r];
+            stride = 1;
+        }
         for (uint32_t n0 = 0; n0 < N; n0 += 128) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (uint32_t p = p0; p < p1; ++p) {
-                const float a = vals[p];
-                const float *brow = B + (size_t)colIdxs[p] * ldb + n0 + lane_id();
+            for (uint32_t j = 0; j < len; ++j) {
+                const uint32_t c = colIdxs[first + (size_t)j * stride];
+                if (SELL && c == kPad) break;
+                const float a = vals[first + (size_t)j * stride];
+                const float *brow = B + (size_t)c * ldb + n0 + lane_id();
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (n0 + 32 * j + lane_id() < N) acc[j] = fmaf(a, brow[32 * j], acc[j]);
+                for (int u = 0; u < 4; ++u)
+                    if (n0 + 32 * u + lane_id() < N) acc[u] = fmaf(a, brow[32 * u], acc[u]);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                if (n0 + 32 * j + lane_id() < N) C[(size_t)r * ldc + n0 + 32 * j + lane_id()] = acc[j];
+            for (int u = 0; u < 4; ++u)
+                if (n0 + 32 * u + lane_id() < N) C[(size_t)r * ldc + n0 + 32 * u + lane_id()] = acc[u];
         }
     }
 }
 
-// one memory pool per device for the tiled copy of B: stream-ordered (cudaMallocAsync / cudaFreeAsync on the caller's stream), so
-// concurrent calls on different streams never share a buffer and nothing synchronises; the pool keeps what it has allocated
 static std::mutex g_tc_pool_mu;
 static cudaMemPool_t g_tc_pools[64] = {};
 // gives the memory the pools hold back to the device (cuspmm_host_pipeline_release); device < 0: all
@@ -833,13 +870,16 @@ static cudaMemPool_t tc_pool(int dev) {
 // N = 512, ~0.04 for N <= 256 (where the fp32 staged kernel does not apply) and for N >= 1024; small problems pay the fixed cost
 // of the three launches and the partly filled last wave: x (1 + 3.7e9 / dense work).  Above the cross-over the gain grows
 // quickly: 1.4-2.7x at 10 %, 2-5.6x from 20 %.
-bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N) {
+// On the sliced-ELL layout (nnz = slots) the kernel gains less -- 25605^2 x 512: 3.45 against 4.31 ms at 10 %, 5.99 / 7.07 at 20 %,
+// 14.6 / 15.6 at 50 %: a row's entries are 128 bytes apart there, so every lane's 4-byte copies fetch whole sectors (8x the bytes)
+// -- and the threshold is 1.6x higher.
+bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool sell) {
     if (M == 0 || K == 0 || N == 0) return false;
     const double Mpad = (double)((M + 511u) / 512u) * 512.0, Npad = (double)((N + 255u) / 256u) * 256.0;
     const double dense = Mpad * (double)K * Npad;
     const double r = (double)nnz * (double)N / dense;
     const double base = N <= 256 ? 0.040 : (N <= 512 ? 0.052 : 0.042);
-    return r >= base * (1.0 + 3.7e9 / dense);
+    return r >= (sell ? 1.6 : 1.0) * base * (1.0 + 3.7e9 / dense);
 }
 
 size_t csr_tc_workspace_bytes(uint32_t K, uint32_t N) {
@@ -847,7 +887,7 @@ size_t csr_tc_workspace_bytes(uint32_t K, uint32_t N) {
     return (size_t)(tilesN * chunks * csrtc::kBBytes + 256);
 }
 
-template <int NCTA>
+template <int NCTA, bool SELL>
 static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
                   const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaMemPool_t pool, cudaStream_t st) {
     using namespace csrtc;
@@ -901,19 +941,20 @@ static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float 
             rc = set_error(CUSPMM_ERR_CUDA, "memset of C failed");
             break;
         }
-        const bool vecA = ((reinterpret_cast<uintptr_t>(colIdxs) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
+        const bool vecA = !SELL && ((reinterpret_cast<uintptr_t>(colIdxs) | reinterpret_cast<uintptr_t>(vals)) & 15) == 0;
         const int vecC = (N % 4 == 0) && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
         // builder threads per row: two lanes per row pay from ~12 % density (25605^2 x 512: 50 %: 6.48 -> 4.79 ms, 10 %: 2.50 = 2.50,
         // 5 %: 2.16 -> 2.26, 2 %: 1.89 -> 2.10: below that the second set of warps only adds fixed work per chunk)
         static const int lprEnv = getenv("CUSPMM_TC_LPR") ? atoi(getenv("CUSPMM_TC_LPR")) : 0;          // tuning hook
         const int lpr = lprEnv == 1 || lprEnv == 2 ? lprEnv : ((double)nnz >= 0.12 * (double)M * (double)K ? 2 : 1);
-        auto kern = lpr == 2 ? (vecA ? csr_tc_kernel<true, NCTA, 2> : csr_tc_kernel<false, NCTA, 2>)
-                             : (vecA ? csr_tc_kernel<true, NCTA, 1> : csr_tc_kernel<false, NCTA, 1>);
-        if (set_smem_once(kern, CF::kSmemTotal) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "cannot reserve %u bytes of shared memory", CF::kSmemTotal); break; }
+        auto kern = lpr == 2 ? (vecA ? csr_tc_kernel<!SELL, NCTA, 2, SELL> : csr_tc_kernel<false, NCTA, 2, SELL>)
+                             : (vecA ? csr_tc_kernel<!SELL, NCTA, 1, SELL> : csr_tc_kernel<false, NCTA, 1, SELL>);
+        const uint32_t smemBytes = lpr == 2 ? Cfg<NCTA, 2>::kSmemTotal : Cfg<NCTA, 1>::kSmemTotal;
+        if (set_smem_once(kern, smemBytes) != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "cannot reserve %u bytes of shared memory", smemBytes); break; }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(pl.grid * NCTA, 1, 1);
         cfg.blockDim = dim3(threads_for(lpr), 1, 1);
-        cfg.dynamicSmemBytes = CF::kSmemTotal;
+        cfg.dynamicSmemBytes = smemBytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -929,7 +970,7 @@ static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float 
             break;
         }
         count_launch();
-        csr_tc_fallback_kernel<<<(unsigned)sm_count() * 4, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc, flag);
+        csr_tc_fallback_kernel<SELL><<<(unsigned)sm_count() * 4, 256, 0, st>>>(rowPtrs, colIdxs, vals, M, B, N, ldb, C, ldc, flag);
         if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of csr_tc_fallback_kernel failed"); break; }
         count_launch();
     } while (0);
@@ -937,9 +978,10 @@ static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float 
     return rc;
 }
 
-// variant 8 of the CSR kernels.  Rows must be sorted by column (as for variants 3, 5, 7).
+// variant 8 of the CSR kernels / variant 6 of the sliced-ELL kernels (sell: rowPtrs = slicePtrs, nnz = slots).  Rows must be sorted
+// by column (as for variants 3, 5, 7).
 int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
-                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaStream_t st) {
+                const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, bool sell, cudaStream_t st) {
     if (K == 0) {
         CUSPMM_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
         return CUSPMM_OK;
@@ -950,8 +992,9 @@ int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
     if (!pool) return set_error(CUSPMM_ERR_CUDA, "no memory pool for the tiled copy of B on device %d", dev);
     // tuning hook: CUSPMM_TC_PAIR=0 runs one CTA per 256-row tile (cta_group::1) instead of CTA pairs on 512-row tiles
     static const int pairEnv = getenv("CUSPMM_TC_PAIR") ? atoi(getenv("CUSPMM_TC_PAIR")) : 1;
-    if (pairEnv) return run_tc<2>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
-    return run_tc<1>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
+    if (sell) return run_tc<2, true>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
+    if (pairEnv) return run_tc<2, false>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
+    return run_tc<1, false>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
 }
 
 } // namespace cuspmm_b200

@@ -127,7 +127,8 @@ int spmm_sell_rows_dispatch(const uint32_t *, const uint32_t *, const float *, u
 
 // variants: 0 auto (the CSR selector applied to the slot count), 1 row kernels (warp / sub-warp per row,
 // nnz-balanced) reading the sliced layout, 2 staged TMA kernel, 3 slice per CTA (A staged through smem),
-// 4 staged with the dual operand path, 5 every B read from tensor memory (CSR variant 7)
+// 4 staged with the dual operand path, 5 every B read from tensor memory (CSR variant 7), 6 tensor cores (CSR variant 8 reading
+// the sliced layout)
 static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals,
                               uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots, const float *B, uint32_t N,
                               size_t ldb, float *C, size_t ldc, int variant, cudaStream_t st) {
@@ -147,6 +148,7 @@ static int spmm_sell_dispatch(const uint32_t *slicePtrs, const uint32_t *colIdxs
     if (variant == 2) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 3, st);
     if (variant == 4) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 5, st);
     if (variant == 5) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 7, st);
+    if (variant == 6) return spmm_sell_rows_dispatch(slicePtrs, colIdxs, vals, M, K, numSlots, B, N, ldb, C, ldc, 8, st);
     if (vok) {
         if (N > 256) sell_vec_kernel<4><<<dim3(slices, (N + 511) / 512), 256, 0, st>>>(slicePtrs, colIdxs, vals, M, B, N, ldb, C, ldc);
         else if (N > 128) sell_vec_kernel<2><<<dim3(slices, 1), 256, 0, st>>>(slicePtrs, colIdxs, vals, M, B, N, ldb, C, ldc);

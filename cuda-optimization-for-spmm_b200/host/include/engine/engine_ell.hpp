@@ -27,6 +27,9 @@ template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper4(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper5(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
+// additive: tensor cores (the CSR tensor kernel reading the sliced layout)
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper6(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref);
 
 template <typename DT, typename MT, typename AccT>
 class EngineELL : public EngineBase {
@@ -40,7 +43,7 @@ class EngineELL : public EngineBase {
     double seqTime = 1.f;
 
     explicit EngineELL(std::string dirPath) {
-        this->numKernels = CUSPMM_ELL_NUM_VARIANTS;   // 5: every C-ABI ELL variant (the reference ships Wrapper2 but sets 1, engine_ell.hpp:32)
+        this->numKernels = CUSPMM_ELL_NUM_VARIANTS;   // 6: every C-ABI ELL variant (the reference ships Wrapper2 but sets 1, engine_ell.hpp:32)
         this->dirPath = dirPath;
         this->fmt = "ELL";
     }
@@ -61,6 +64,7 @@ class EngineELL : public EngineBase {
         if (num == 3) return spmmELLWrapper3<DT, MT, AccT>(ma, mb, mc);
         if (num == 4) return spmmELLWrapper4<DT, MT, AccT>(ma, mb, mc);
         if (num == 5) return spmmELLWrapper5<DT, MT, AccT>(ma, mb, mc);
+        if (num == 6) return spmmELLWrapper6<DT, MT, AccT>(ma, mb, mc);
         if (num == -1) return spmmELLWrapper1<DT, MT, AccT>(ma, mb, mc);
         throw std::runtime_error("Not implemented");
     }

@@ -291,6 +291,10 @@ template <typename DT, typename MT, typename AccT>
 DenseMatrix<DT, MT> *spmmELLWrapper5(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref) {
     return ellWrapper<DT, MT, AccT>(5, "sell32_all_tmem_quad", a, b, ref);
 }
+template <typename DT, typename MT, typename AccT>
+DenseMatrix<DT, MT> *spmmELLWrapper6(SparseMatrixELL<DT, MT> *a, DenseMatrix<DT, MT> *b, DenseMatrix<DT, MT> *ref) {
+    return ellWrapper<DT, MT, AccT>(6, "sell32_tensor_split", a, b, ref);
+}
 
 // ------------------------------------------------------------------------------- BSR wrappers
 template <typename DT, typename MT>
@@ -367,6 +371,7 @@ template Dn *spmmELLWrapper2<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);
 template Dn *spmmELLWrapper3<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);
 template Dn *spmmELLWrapper4<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);
 template Dn *spmmELLWrapper5<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);
+template Dn *spmmELLWrapper6<F, U, A>(SparseMatrixELL<F, U> *, Dn *, Dn *);
 template Dn *spmmBSRWrapper1<F, U, A>(SparseMatrixBSR<F, U> *, Dn *, Dn *);
 template Dn *spmmBSRWrapper2<F, U, A>(SparseMatrixBSR<F, U> *, Dn *, Dn *);
 template Dn *spmmBSRWrapper3<F, U, A>(SparseMatrixBSR<F, U> *, Dn *, Dn *);

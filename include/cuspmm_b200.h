@@ -131,10 +131,12 @@ int cuspmm_spmm_coo(const uint32_t *rowIdxs_dev, const uint32_t *colIdxs_dev, co
  * s is W_s slots wide, slot-major: entry j of row s*32+i at slicePtrs[s] + j*32 + i;
  * padding colIdx 0xFFFFFFFF / value 0.  Replaces spmmELLWrapper1/2 / spmmELLK1/2
  * (include/engine/engine_ell.hpp:15-19, src/spmm/ell/spmm_ell_k{1,2}.cu). */
-#define CUSPMM_ELL_NUM_VARIANTS 5 /* 1 row kernels (warp / sub-warp per row); 2 staged (B tiles via TMA bulk
+#define CUSPMM_ELL_NUM_VARIANTS 6 /* 1 row kernels (warp / sub-warp per row); 2 staged (B tiles via TMA bulk
                                      copies); 3 slice per CTA with the slots staged through shared memory;
                                      4 staged with the dual operand path (CSR variant 5 on the sliced layout);
-                                     5 every B read from tensor memory (CSR variant 7 on the sliced layout) */
+                                     5 every B read from tensor memory (CSR variant 7 on the sliced layout);
+                                     6 tensor cores (CSR variant 8 on the sliced layout: fp32-grade, not bit-identical
+                                     to 1..5; what variant 0 resolves to from ~5 % density, see cuspmm_set_csr_tensor_mode) */
 int cuspmm_spmm_sell(const uint32_t *slicePtrs_dev, const uint32_t *colIdxs_dev, const float *vals_dev,
                      uint32_t M, uint32_t K, uint32_t sliceH, uint32_t numSlots /* = slicePtrs[numSlices] */,
                      const float *B_dev, uint32_t N, size_t ldb,

@@ -87,7 +87,7 @@ def test_cli_all_formats_on_reference_fixtures(case):
         else:
             assert r["correct"] == "1", r
         assert r["denseOrdering"] == "ROW_MAJOR"
-    assert [r["kernelType"] for r in by_fmt["ELL"]] == ["0", "1", "2", "3", "4", "5"]     # every C-ABI ELL variant
+    assert [r["kernelType"] for r in by_fmt["ELL"]] == ["0", "1", "2", "3", "4", "5", "6"]     # every C-ABI ELL variant
 
 
 @pytest.mark.gpu
@@ -140,7 +140,7 @@ def test_cli_on_generated_directory(tmp_path):
     subprocess.run(["python", os.path.join(ROOT, "scripts", "gen_data.py"), d, "--rows", "1024", "--cols", "768", "--density", "0.1",
                     "--N", "512", "--range", "-1", "1", "--bsr-block", "16"], check=True, capture_output=True)
     recs = records(run("--csr", "--coo", "--ell", "--bsr", "-d", d, "--iters", "2").stdout)
-    assert len(recs) == 10 + 4 + 6 + 4         # CSR 0..8 + cuSPARSE, COO 0..2 + cuSPARSE, ELL 0..5, BSR 0..3
+    assert len(recs) == 10 + 4 + 7 + 4         # CSR 0..8 + cuSPARSE, COO 0..2 + cuSPARSE, ELL 0..6, BSR 0..3
     for r in recs:
         if r["format"] == "BSR" and r["kernelType"] in ("2", "3"):
             # bf16/fp16 operand rounding (2^-9 / 2^-12 per operand) is judged with its own tolerance in

@@ -70,6 +70,9 @@ def test_random_shapes_all_variants(b, M, K, N, d, skew, seed):
             assert "status 3" in str(e) and v in (2, 4, 5), (v, str(e))
             continue
         assert (got == base).all().item(), ("ell", v)
+    # ELL 6 = the tensor-core kernel on the sliced layout: the tolerance, not bit-identity
+    got = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=6)
+    assert orc.max_rel_err(got.cpu().numpy(), ref, den) <= TOL, "ell 6"
     # host-buffer entry points (pipelined H2D / kernel / D2H)
     C_h = torch.empty((M, N), dtype=torch.float32).pin_memory()
     b.spmm_csr_host(b.pinned(a.rowPtrs), b.pinned(a.colIdxs), b.pinned(a.vals), M, K, b.pinned(B), C_h)

@@ -243,7 +243,7 @@ def test_selector_rules(b):
     assert sel(4096, 4096, 1678023, 512) == 8 and sel(4096, 4096, 838880, 512) != 8
     assert sel(3200, 25605, 8196778, 512) == 8                   # an 8-GPU row panel of the BASELINE matrix
     assert sel(300, 200, 6000, 512) != 8                         # small: fixed costs
-    assert sel(25605, 25605, 65571195, 512, sell=True) != 8      # the kernel reads CSR, not sliced ELL
+    assert sel(25605, 25605, 65571195, 512, sell=True) == 8      # the kernel also reads the sliced-ELL layout
     assert sel(25605, 25605, 65571195, 510) in (1, 2, 4, 8)
     prev = b.set_csr_tensor_mode(0)
     try:
@@ -290,3 +290,42 @@ def test_variant0_paths_with_tensor_selection(b, wl):
     finally:
         plan.close()
     torch.cuda.set_device(0)
+
+
+# ------------------------------------------------------------------ the same kernel reading sliced ELL (ELL variant 6)
+@pytest.mark.parametrize("M,K,N,d,skew", [(1, 1, 512, 1.0, False), (57, 129, 512, 0.10, False), (300, 500, 260, 0.5, False),
+                                          (1000, 4096, 512, 0.01, False), (2000, 1500, 512, 0.03, True), (300, 257, 1024, 0.0, False),
+                                          (3000, 2500, 21, 0.3, True), (5000, 3000, 512, 0.2, False)])
+def test_tensor_kernel_on_sliced_ell(b, M, K, N, d, skew):
+    """Rows of very different lengths inside a slice (skew), padding entries, slices past M, both builder layouts."""
+    a = random_csr(M, K, d, seed=500 + M + N, skew=skew)
+    B = np.random.default_rng(7).uniform(-1, 1, (K, N)).astype(np.float32)
+    ref, den = orc.spmm_csr(a, B, omp=True), orc.absprod_csr(a, B)
+    rp, ci, va = dev_csr(b, a)
+    sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
+    got = b.spmm_sell(sp, sc, sv, M, K, b.dev_f32(B), variant=6).cpu().numpy()
+    assert np.isfinite(got).all()
+    assert orc.max_rel_err(got, ref, den) <= TOL
+
+
+def test_sliced_ell_selector_and_non_finite_B(b, wl):
+    """4096^2 at 20 %: ELL variant 0 resolves to the tensor kernel; a NaN row of B stays in the rows that reference it."""
+    import torch
+    M = K = 4096
+    N = 512
+    rp, ci, va = wl.gen_csr_device(M, K, 0.20, seed=43)
+    Bd = wl.gen_dense_device(K, N, seed=44)
+    sp, sc, sv = b.csr_to_sell(rp, ci, va, M)
+    assert b.csr_selected_variant(M, K, int(sc.numel()), N, sell=True) == 8
+    ref = b.spmm_csr(rp, ci, va, M, K, Bd, variant=1)
+    den = b.spmm_csr(rp, ci, va.abs(), M, K, Bd.abs(), variant=1).clamp_min(1e-30)
+    c0 = b.spmm_sell(sp, sc, sv, M, K, Bd, variant=0)
+    assert ((c0 - ref).abs() / den).max().item() <= 2e-6
+    assert not (c0 == ref).all().item()                          # the tensor kernel ran, not an fp32 one
+    Bn = Bd.clone()
+    Bn[100, :] = float("nan")
+    cn = b.spmm_sell(sp, sc, sv, M, K, Bn, variant=6)
+    rn = b.spmm_csr(rp, ci, va, M, K, Bn, variant=1)
+    assert (torch.isnan(cn) == torch.isnan(rn)).all().item()
+    ok = ~torch.isnan(rn)
+    assert ((cn[ok] - rn[ok]).abs() / den[ok]).max().item() <= 2e-6
