@@ -329,3 +329,26 @@ def test_sliced_ell_selector_and_non_finite_B(b, wl):
     assert (torch.isnan(cn) == torch.isnan(rn)).all().item()
     ok = ~torch.isnan(rn)
     assert ((cn[ok] - rn[ok]).abs() / den[ok]).max().item() <= 2e-6
+
+
+def test_mgpu_plans_with_the_tensor_kernel(b):
+    """Multi-GPU plans (n = 1, and every count the box has) with the tensor kernel forced: CSR variant 8, COO 2 -> selector, sliced ELL 6,
+    with and without the gather into GPU 0 (panels on other GPUs are computed locally and sent with one peer copy)."""
+    import torch
+    a = random_csr(4100, 1300, 0.25, seed=81, skew=False)
+    N = 256
+    B = np.random.default_rng(82).uniform(-1, 1, (1300, N)).astype(np.float32)
+    ref, den = orc.spmm_csr(a, B, omp=True), orc.absprod_csr(a, B)
+    coo, s = orc.csr_to_coo(a), orc.csr_to_sell(a)
+    counts = sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()})
+    for n in counts:
+        for fmt, arrs, v in (("csr", (a.rowPtrs, a.colIdxs, a.vals), 8), ("sell", (s.slicePtrs, s.colIdxs, s.vals), 6)):
+            plan = b.MgpuPlan(n, arrs[0], arrs[1], arrs[2], a.M, a.K, N, fmt=fmt)
+            try:
+                plan.set_B(B)
+                for gather in (False, True):
+                    assert plan.run(variant=v, gather=gather, iters=2) > 0
+                    assert orc.max_rel_err(plan.get_C(), ref, den) <= TOL, (fmt, n, gather)
+            finally:
+                plan.close()
+    torch.cuda.set_device(0)
