@@ -94,7 +94,7 @@ def main():
             print(json.dumps({"config": name, "cusparse_error": str(ex)[:100]}), flush=True)
         kernels = [("csr", v, (lambda v=v: b.spmm_csr(rp, ci, va, M, K, Bd, variant=v, out=Cd))) for v in (0, 1, 2, 3, 5, 7, 8)]
         kernels += [("coo", v, (lambda v=v: b.spmm_coo(rows, ci, va, M, K, Bd, variant=v, out=Cd))) for v in (1, 2)]
-        kernels += [("ell", v, (lambda v=v: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=v, out=Cd))) for v in (0, 1, 2, 3, 4, 5)]
+        kernels += [("ell", v, (lambda v=v: b.spmm_sell(sp, sc, sv, M, K, Bd, variant=v, out=Cd))) for v in (0, 1, 2, 3, 4, 5, 6)]
         for fmt, v, fn in kernels:
             try:
                 med, mn = timeit(fn, cold)
