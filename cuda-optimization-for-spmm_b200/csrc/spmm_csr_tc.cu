@@ -60,6 +60,7 @@
 #include "tmem_common.cuh"
 
 #include <cuda_bf16.h>
+#include <cub/device/device_scan.cuh>
 
 namespace cuspmm_b200 {
 namespace csrtc {
@@ -870,16 +871,15 @@ static cudaMemPool_t tc_pool(int dev) {
 // N = 512, ~0.04 for N <= 256 (where the fp32 staged kernel does not apply) and for N >= 1024; small problems pay the fixed cost
 // of the three launches and the partly filled last wave: x (1 + 3.7e9 / dense work).  Above the cross-over the gain grows
 // quickly: 1.4-2.7x at 10 %, 2-5.6x from 20 %.
-// On the sliced-ELL layout (nnz = slots) the kernel gains less -- 25605^2 x 512: 3.45 against 4.31 ms at 10 %, 5.99 / 7.07 at 20 %,
-// 14.6 / 15.6 at 50 %: a row's entries are 128 bytes apart there, so every lane's 4-byte copies fetch whole sectors (8x the bytes)
-// -- and the threshold is 1.6x higher.
+// On the sliced-ELL layout (nnz = slots) the slices are compacted into CSR first (two passes over A: +0.35 ms at 10 %, +1.8 ms at
+// 50 % on 25605^2): 2.58 against 4.31 ms (fp32 ELL kernels) at 10 %, 4.09 / 9.82 at 30 %, 5.65 / 15.5 at 50 %; threshold 1.25x higher.
 bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool sell) {
     if (M == 0 || K == 0 || N == 0) return false;
     const double Mpad = (double)((M + 511u) / 512u) * 512.0, Npad = (double)((N + 255u) / 256u) * 256.0;
     const double dense = Mpad * (double)K * Npad;
     const double r = (double)nnz * (double)N / dense;
     const double base = N <= 256 ? 0.040 : (N <= 512 ? 0.052 : 0.042);
-    return r >= (sell ? 1.6 : 1.0) * base * (1.0 + 3.7e9 / dense);
+    return r >= (sell ? 1.25 : 1.0) * base * (1.0 + 3.7e9 / dense);
 }
 
 size_t csr_tc_workspace_bytes(uint32_t K, uint32_t N) {
@@ -978,6 +978,89 @@ static int run_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float 
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------- sliced ELL -> CSR on the device
+// The tensor kernel reads sliced ELL directly (SELL = true), but a row's entries are 128 bytes apart there and the per-row ring of
+// 4-byte copies fetches a 32-byte sector for each of them: 3.4 ms against 2.2 on CSR at 10 % density, 14.1 against 3.85 at 50 %.
+// Compacting the slices into CSR first (two passes over A at HBM speed, tiles transposed through shared memory so that both the
+// reads and the writes are 128-byte lines) and running the CSR kernel is faster at every density where the tensor kernel is chosen.
+__global__ void __launch_bounds__(256)
+sell_row_lengths_kernel(const uint32_t *__restrict__ slicePtrs, const uint32_t *__restrict__ colIdxs, uint32_t M, uint32_t *__restrict__ lens) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > M) return;
+    if (r == M) { lens[M] = 0; return; }
+    const uint32_t sb = slicePtrs[r >> 5], w = (slicePtrs[(r >> 5) + 1] - sb) >> 5;
+    const size_t first = (size_t)sb + (r & 31u);
+    uint32_t lo = 0, hi = w;                                  // first padding entry (columns ascend, padding = 0xFFFFFFFF)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (colIdxs[first + 32u * (size_t)mid] != kPad) lo = mid + 1; else hi = mid;
+    }
+    lens[r] = lo;
+}
+// one CTA per slice, 4 warps; a warp moves tiles of 32 slots x 32 rows: coalesced reads along the rows of the slice, transposed in
+// shared memory, coalesced writes along the entries of a row
+__global__ void __launch_bounds__(128)
+sell_compact_kernel(const uint32_t *__restrict__ slicePtrs, const uint32_t *__restrict__ colIdxs, const float *__restrict__ vals, uint32_t M,
+                    const uint32_t *__restrict__ rowPtrs, uint32_t *__restrict__ outCols, float *__restrict__ outVals) {
+    __shared__ uint32_t tc[4][32][33];
+    __shared__ float tv[4][32][33];
+    const uint32_t s = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t sb = slicePtrs[s], w = (slicePtrs[s + 1] - sb) >> 5;
+    const uint32_t r = s * 32 + lane;
+    const uint32_t myStart = r < M ? rowPtrs[r] : 0u, myLen = r < M ? rowPtrs[r + 1] - myStart : 0u;
+    for (uint32_t j0 = warp * 32; j0 < w; j0 += 4 * 32) {
+#pragma unroll 4
+        for (uint32_t i = 0; i < 32; ++i) {
+            const bool in = j0 + i < w;
+            const size_t at = (size_t)sb + (size_t)(j0 + i) * 32u + lane;
+            tc[warp][i][lane] = in ? colIdxs[at] : kPad;
+            tv[warp][i][lane] = in ? vals[at] : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (uint32_t rr = 0; rr < 32; ++rr) {                // row rr of the slice: lane = entry j0 + lane
+            const uint32_t start = __shfl_sync(0xFFFFFFFFu, myStart, rr), len = __shfl_sync(0xFFFFFFFFu, myLen, rr);
+            if (j0 + lane < len) {
+                outCols[(size_t)start + j0 + lane] = tc[warp][lane][rr];
+                outVals[(size_t)start + j0 + lane] = tv[warp][lane][rr];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static int sell_to_csr_then_tc(const uint32_t *slicePtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t slots,
+                               const float *B, uint32_t N, size_t ldb, float *C, size_t ldc, cudaMemPool_t pool, cudaStream_t st) {
+    // temporaries from the stream-ordered pool: row pointers, and column / value arrays sized by the slot count (an upper bound of
+    // nnz that needs no host round trip)
+    const size_t rpBytes = ((size_t)(M + 1) * 4 + 255) & ~(size_t)255, arrBytes = ((size_t)slots * 4 + 255) & ~(size_t)255;
+    size_t scanBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)(M + 1), st);
+    scanBytes = (scanBytes + 255) & ~(size_t)255;
+    unsigned char *tmp = nullptr;
+    CUSPMM_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&tmp), 2 * rpBytes + 2 * arrBytes + scanBytes, pool, st));
+    uint32_t *lens = reinterpret_cast<uint32_t *>(tmp), *rowPtrs = reinterpret_cast<uint32_t *>(tmp + rpBytes);
+    uint32_t *cols = reinterpret_cast<uint32_t *>(tmp + 2 * rpBytes);
+    float *v = reinterpret_cast<float *>(tmp + 2 * rpBytes + arrBytes);
+    void *scanTmp = tmp + 2 * rpBytes + 2 * arrBytes;
+    int rc = CUSPMM_OK;
+    do {
+        sell_row_lengths_kernel<<<(M + 1 + 255) / 256, 256, 0, st>>>(slicePtrs, colIdxs, M, lens);
+        if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of sell_row_lengths_kernel failed"); break; }
+        count_launch();
+        if (cub::DeviceScan::ExclusiveSum(scanTmp, scanBytes, lens, rowPtrs, (int)(M + 1), st) != cudaSuccess) {
+            rc = set_error(CUSPMM_ERR_CUDA, "prefix sum of the row lengths failed");
+            break;
+        }
+        sell_compact_kernel<<<(M + 31) / 32, 128, 0, st>>>(slicePtrs, colIdxs, vals, M, rowPtrs, cols, v);
+        if (cudaGetLastError() != cudaSuccess) { rc = set_error(CUSPMM_ERR_CUDA, "launch of sell_compact_kernel failed"); break; }
+        count_launch();
+        rc = run_tc<2, false>(rowPtrs, cols, v, M, K, slots, B, N, ldb, C, ldc, pool, st);
+    } while (0);
+    cudaFreeAsync(tmp, st);
+    return rc;
+}
+
 // variant 8 of the CSR kernels / variant 6 of the sliced-ELL kernels (sell: rowPtrs = slicePtrs, nnz = slots).  Rows must be sorted
 // by column (as for variants 3, 5, 7).
 int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *vals, uint32_t M, uint32_t K, uint32_t nnz,
@@ -992,7 +1075,12 @@ int spmm_csr_tc(const uint32_t *rowPtrs, const uint32_t *colIdxs, const float *v
     if (!pool) return set_error(CUSPMM_ERR_CUDA, "no memory pool for the tiled copy of B on device %d", dev);
     // tuning hook: CUSPMM_TC_PAIR=0 runs one CTA per 256-row tile (cta_group::1) instead of CTA pairs on 512-row tiles
     static const int pairEnv = getenv("CUSPMM_TC_PAIR") ? atoi(getenv("CUSPMM_TC_PAIR")) : 1;
-    if (sell) return run_tc<2, true>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
+    if (sell) {
+        // tuning hook: CUSPMM_TC_SELL_DIRECT=1 lets the tensor kernel read the sliced layout itself instead of compacting it first
+        static const int direct = getenv("CUSPMM_TC_SELL_DIRECT") ? atoi(getenv("CUSPMM_TC_SELL_DIRECT")) : 0;
+        if (direct) return run_tc<2, true>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
+        return sell_to_csr_then_tc(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
+    }
     if (pairEnv) return run_tc<2, false>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
     return run_tc<1, false>(rowPtrs, colIdxs, vals, M, K, nnz, B, N, ldb, C, ldc, pool, st);
 }
