@@ -867,10 +867,11 @@ static cudaMemPool_t tc_pool(int dev) {
 
 // Does the tensor-core kernel (work ~ Mpad x K x Npad, independent of nnz) beat the fp32 kernels (work ~ nnz x N)?
 // r = nnz x N / (Mpad x K x Npad) is the useful fraction of the dense work.  Measured cross-over (profiles/r02_tc_sweep.jsonl,
-// 117 shapes: squares 4096..25605, N 128..2048, 2..50 % dense, row panels of the BASELINE matrix, FFN shapes): r ~ 0.05 at
-// N = 512, ~0.04 for N <= 256 (where the fp32 staged kernel does not apply) and for N >= 1024; small problems pay the fixed cost
-// of the three launches and the partly filled last wave: x (1 + 3.7e9 / dense work).  Above the cross-over the gain grows
-// quickly: 1.4-2.7x at 10 %, 2-5.6x from 20 %.
+// 117 shapes: squares 4096..25605, N 128..2048, 2..50 % dense, row panels of the BASELINE matrix, FFN shapes; final kernel):
+// r ~ 0.036 at N = 512, ~0.028 for N <= 256 (where the fp32 staged kernel does not apply) and for N >= 1024; small problems pay the
+// fixed cost of the launches and the partly filled last wave: x (1 + 3.7e9 / dense work).  With these thresholds the choice is
+// within 2 % of the faster kernel on 115 of the 117 shapes.  Above the cross-over the gain grows quickly: 1.2-3.0x at 10 %,
+// 2-4.9x at 20 %, 3-8.9x at 50 %.
 // On the sliced-ELL layout (nnz = slots) the slices are compacted into CSR first (two passes over A: +0.35 ms at 10 %, +1.8 ms at
 // 50 % on 25605^2): 2.58 against 4.31 ms (fp32 ELL kernels) at 10 %, 4.09 / 9.82 at 30 %, 5.65 / 15.5 at 50 %; threshold 1.25x higher.
 bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool sell) {
@@ -878,7 +879,7 @@ bool tc_kernel_wins(uint32_t M, uint32_t K, uint64_t nnz, uint32_t N, bool sell)
     const double Mpad = (double)((M + 511u) / 512u) * 512.0, Npad = (double)((N + 255u) / 256u) * 256.0;
     const double dense = Mpad * (double)K * Npad;
     const double r = (double)nnz * (double)N / dense;
-    const double base = N <= 256 ? 0.040 : (N <= 512 ? 0.052 : 0.042);
+    const double base = N <= 256 ? 0.028 : (N <= 512 ? 0.036 : 0.029);
     return r >= (sell ? 1.25 : 1.0) * base * (1.0 + 3.7e9 / dense);
 }
 
